@@ -1,0 +1,150 @@
+/* scb200.h -- C ABI of libscb200.so, the B200 (sm_100a) implementation of the
+ * sparsify-clip contrastive-loss hot path.
+ *
+ * The reference (noostale/sparsify-clip) has no FFI / plugin interface: its hot path is
+ * six Python functions executed by PyTorch eager ops.  The drop-in
+ * boundary is therefore the Python signatures in sparsify_clip_b200/losses.py; those
+ * call the entry points below through ctypes.  Each entry point cites the reference
+ * lines whose arithmetic it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless noted;
+ *  - the library never allocates or frees device memory and keeps no global state
+ *    beyond the lazily resolved cuTensorMapEncodeTiled driver entry point;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs
+ *    no host synchronisation and is CUDA-graph capturable;
+ *  - return value: 0 ok; <0 invalid argument (SCB_E_*); >0 a cudaError_t.
+ *    scb_last_error() returns a thread-local message for the last failure;
+ *  - matrices are row-major [n, D] with leading dimension ld (elements);
+ *  - dtype: SCB_F32 / SCB_BF16 / SCB_F16;
+ *  - path:  SCB_PATH_SIMT  fp32 CUDA-core kernels (any dtype, any D; the exact path used
+ *                          for fp32 inputs and the "tf32-off" parity gate),
+ *           SCB_PATH_TC    TMA + tcgen05/TMEM tensor-core kernels (bf16/fp16, D % 8 == 0,
+ *                          16-byte aligned rows);
+ *  - "jparts": the column sweep of a pass may be split into `jparts` contiguous parts so
+ *    that the grid fills 148 SMs; each part writes its own partial result and the
+ *    *_finalize / *_combine entry points add the partials in a fixed order
+ *    (deterministic, no float atomics).  A pass writes nsub = scb_pass_nsub(path)
+ *    sub-partials per part for the per-row statistics.
+ */
+#ifndef SCB200_H_
+#define SCB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCB_F32 0
+#define SCB_BF16 1
+#define SCB_F16 2
+
+#define SCB_PATH_SIMT 0
+#define SCB_PATH_TC 1
+
+#define SCB_E_ARG (-1)       /* bad pointer / size / alignment */
+#define SCB_E_DTYPE (-2)     /* dtype not supported on this path */
+#define SCB_E_SHAPE (-3)     /* shape not supported on this path */
+#define SCB_E_DRIVER (-4)    /* cuTensorMapEncodeTiled unavailable / failed */
+
+int scb_version(void);
+const char* scb_last_error(void);
+/* number of per-row statistic sub-partials each column part writes (1 SIMT, 2 TC) */
+int scb_pass_nsub(int path);
+/* debug/tuning knobs for the TC path: bit0 = keep the weight tile in TMEM (TS-mode MMA)
+ * instead of shared memory.  Returns the previous value. */
+int scb_set_tc_flags(int flags);
+
+/* ------------------------------------------------------------------ row-wise kernels */
+
+/* out[i] = sum_d X[i,d]^2 (fp32).  Used for d2_ij = n_i + n_j - 2 x_i.x_j, the Gram form
+ * of torch.pdist at sparsify_clip.py:161. */
+int scb_row_sqnorm(const void* X, int64_t n, int D, int64_t ld, int dtype, float* out, void* stream);
+
+/* out[i] = A[i,:] . B[i,:] (fp32): the diagonal logits of sparsify_clip.py:119 before /tau. */
+int scb_row_dot(const void* A, const void* B, int64_t n, int D, int64_t ldA, int64_t ldB, int dtype,
+                float* out, void* stream);
+
+/* L_align, sparsify_clip.py:186-187 with alpha = 2:
+ * row_out[i] = ||x_i - y_i||^2.  The mean is taken by scb_sum + a host scalar. */
+int scb_lalign_rows(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
+                    float* row_out, void* stream);
+/* dX[i,:] (+)= scale * (x_i - y_i), dY[i,:] (+)= -scale * (x_i - y_i); scale = host_scale *
+ * (dev_scale ? *dev_scale : 1).  Gradient of the line above (2/B folded into scale). */
+int scb_lalign_bwd(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
+                   float host_scale, const float* dev_scale, int accumulate, float* dX, float* dY, void* stream);
+
+/* c = normalize((a+b)/2, eps=1e-12): compute_centroids_only (sparsify_clip.py:334-355)
+ * followed by F.normalize at its call sites (:803-805 ...).  C_out has dtype `out_dtype`;
+ * inv_norm[i] = 1/max(||m_i||,1e-12). */
+int scb_centroid_fwd(const void* A, const void* B, int64_t n, int D, int64_t ldA, int64_t ldB, int dtype,
+                     void* C_out, int out_dtype, float* inv_norm, void* stream);
+/* given dC (fp32 [n,D]): dm = (dC - c (c.dC)) * inv_norm; dA (+)= scale*dm/2; dB likewise. */
+int scb_centroid_bwd(const void* A, const void* B, int64_t n, int D, int64_t ldA, int64_t ldB, int dtype,
+                     const float* dC, const float* inv_norm, float host_scale, const float* dev_scale,
+                     int accumulate, float* dA, float* dB, void* stream);
+
+/* pre-loss normalise e/||e|| (no eps), sparsify_clip.py:772-773, and its backward
+ * dx = (g - xhat (xhat.g)) / ||x||. */
+int scb_normalize_fwd(const void* X, int64_t n, int D, int64_t ld, int dtype, void* Y, int out_dtype,
+                      float* inv_norm, void* stream);
+int scb_normalize_bwd(const void* X, int64_t n, int D, int64_t ld, int dtype, const float* dY,
+                      const float* inv_norm, float* dX, void* stream);
+
+/* deterministic two-stage sum of n floats into out[0] (scratch >= 1024 floats). */
+int scb_sum(const float* x, int64_t n, float* scratch, float* out, void* stream);
+
+/* ------------------------------------------------------------- B x B passes (never materialised) */
+
+/* Row log-sum-exp partials of S = scale * A.Bm^T  (sparsify_clip.py:119-120 + the
+ * log_softmax inside F.cross_entropy at :127/:129; call with (I,T) for rows and (T,I)
+ * for columns).  Writes part_m/part_l [jparts*nsub][nA] (log2-domain running max and sum). */
+int scb_lse_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
+                 int dtype, float scale, int jparts, float* part_m, float* part_l, int path, void* stream);
+/* lse[i] = natural-log LSE from nparts partials. */
+int scb_lse_combine(const float* part_m, const float* part_l, int nparts, int64_t n, float* lse, void* stream);
+
+/* Backward of the anchor loss w.r.t. the rows of A (sparsify_clip.py:110-132; the
+ * recompute replaces autograd's saved B x B tensors):
+ *   out[p][i,:]  = sum_{j in part p, j != i+diag_off} (e^{s_ij - row_lse_i} + e^{s_ij - col_lse_j}) Bm[j,:]
+ *   ws[p*nsub+q][i] = sum_j (same weights, diagonal INCLUDED) * (A_i.Bm_j)        (for d/dtau)
+ * s_ij = scale*A_i.Bm_j.  Call with (I,T,row_lse=r,col_lse=c) for dI and (T,I,c,r) for dT.
+ * ws may be NULL. */
+int scb_anchor_grad_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
+                         int dtype, float scale, const float* row_lse, const float* col_lse, int64_t diag_off,
+                         int jparts, float* out, float* ws, int path, void* stream);
+/* dA[i,:] (+)= s * ( sum_p out[p][i,:] + (e^{sc*diag_i - row_lse_i} + e^{sc*diag_i - col_lse_i} - 2) * V[i,:] ),
+ * s = host_scale * (dev_scale ? *dev_scale : 1); V = the paired rows of the other modality. */
+int scb_anchor_grad_finalize(const float* out, int jparts, int64_t n, int D, const void* V, int64_t ldV, int dtype,
+                             const float* row_lse, const float* col_lse_rows, const float* diag, float scale,
+                             float host_scale, const float* dev_scale, int accumulate, float* dA, void* stream);
+
+/* Single-pass L_unif forward+backward core (sparsify_clip.py:159-164; replaces torch.pdist,
+ * the 7 element-wise passes over its output and _pdist_backward):
+ *   w_ij = exp(-t (n_i + n_j - 2 x_i.x_j)),  w_ij = 0 where global row == global column
+ *   U[p][i,:] = sum_{j in part p} w~_ij Xall[j,:]      (w~ = w rounded to the MMA operand type on TC)
+ *   rq[.][i]  = sum_j w~_ij         rs[.][i] = sum_j w_ij (fp32)
+ * Xr = the nR local rows (global row index = row_offset + i), Xall = all nAll rows. */
+int scb_lunif_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
+                   int dtype, float t, const float* sqn_r, const float* sqn_all, int64_t row_offset,
+                   int jparts, float* U, float* rq, float* rs, int path, void* stream);
+/* forward-only variant (no gradient needed): rs only. */
+int scb_lunif_sum_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
+                       int dtype, float t, const float* sqn_r, const float* sqn_all, int64_t row_offset,
+                       int jparts, float* rs, int path, void* stream);
+/* dX[i,:] (+)= s * ( (sum_q rq[q][i]) * x_i - sum_p U[p][i,:] ),  s = host_scale * *dev_scale
+ * (dev_scale carries -2t/Ssum, which depends on a device-side reduction). */
+int scb_lunif_grad_finalize(const float* U, int jparts, const float* rq, int nparts_rq, int64_t n, int D,
+                            const void* X, int64_t ld, int dtype, float host_scale, const float* dev_scale,
+                            int accumulate, float* dX, void* stream);
+
+/* sparsify_loss (sparsify_clip.py:166-176), forward: row partial sums of
+ * (x_i.x_j - (2 delta_ij - 1))^2 over j; rs [jparts*nsub][nR]. */
+int scb_sparsify_sum_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
+                          int dtype, int64_t row_offset, int jparts, float* rs, int path, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCB200_H_ */

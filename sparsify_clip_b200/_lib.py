@@ -1,0 +1,86 @@
+"""ctypes binding of libscb200.so (C ABI declared in include/scb200.h).
+
+The library is the product: if it cannot be loaded this module raises -- there is no CPU
+or PyTorch fallback anywhere in the package.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libscb200.so")
+HEADER = os.path.join(os.path.dirname(HERE), "include", "scb200.h")
+
+SCB_F32, SCB_BF16, SCB_F16 = 0, 1, 2
+PATH_SIMT, PATH_TC = 0, 1
+
+_vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+
+# name -> argtypes, in the order of include/scb200.h
+SIGNATURES = {
+    "scb_version": [],
+    "scb_pass_nsub": [_i32],
+    "scb_set_tc_flags": [_i32],
+    "scb_row_sqnorm": [_vp, _i64, _i32, _i64, _i32, _vp, _vp],
+    "scb_row_dot": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _vp],
+    "scb_lalign_rows": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _vp],
+    "scb_lalign_bwd": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _i32, _vp, _vp, _vp],
+    "scb_centroid_fwd": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _i32, _vp, _vp],
+    "scb_centroid_bwd": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _i32, _vp, _vp, _vp],
+    "scb_normalize_fwd": [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _vp, _vp],
+    "scb_normalize_bwd": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
+    "scb_sum": [_vp, _i64, _vp, _vp, _vp],
+    "scb_lse_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _i32, _vp],
+    "scb_lse_combine": [_vp, _vp, _i32, _i64, _vp, _vp],
+    "scb_anchor_grad_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp],
+    "scb_anchor_grad_finalize": [_vp, _i32, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i32, _vp, _vp],
+    "scb_lunif_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp],
+    "scb_lunif_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _i32, _vp],
+    "scb_lunif_grad_finalize": [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _i64, _i32, _f32, _vp, _i32, _vp, _vp],
+    "scb_sparsify_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _i64, _i32, _vp, _i32, _vp],
+}
+
+_lib = None
+
+
+def header_symbols():
+    """Every function name include/scb200.h declares (used by the CPU symbol test)."""
+    with open(HEADER) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(scb_[a-z0-9_]+)\s*\(", src)))
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed and nvcc is present) and type the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing:
+        try:
+            from . import build as _build
+            if _build.needs_build():
+                _build.build()
+        except Exception as exc:  # no nvcc on this box: a prebuilt .so must already be there
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(f"libscb200.so is missing and could not be built: {exc}") from exc
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m sparsify_clip_b200.build` "
+                           "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.scb_last_error.argtypes = []
+    lib.scb_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc == 0:
+        return
+    msg = load().scb_last_error().decode(errors="replace")
+    if rc < 0:
+        raise ValueError(f"scb200 {what}: {msg} (code {rc})")
+    raise RuntimeError(f"scb200 {what}: CUDA error {rc}: {msg}")

@@ -1,0 +1,278 @@
+"""CUDA backend: torch tensors in, libscb200.so (C ABI, include/scb200.h) underneath.
+
+PyTorch is only plumbing here: it owns the device buffers and the stream.  All arithmetic
+on the hot path happens in the library's kernels.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import PATH_SIMT, PATH_TC, SCB_BF16, SCB_F16, SCB_F32, check
+
+_DT = {torch.float32: SCB_F32, torch.bfloat16: SCB_BF16, torch.float16: SCB_F16}
+
+# How fp32 inputs are computed: "exact" = fp32 CUDA-core kernels (parity gate: 1e-5 on gradients),
+# "bf16" = round once to bf16 and use the tensor-core path.
+_fp32_mode = "exact"
+_force_path = None  # testing hook: PATH_SIMT / PATH_TC / None
+
+
+def set_fp32_mode(mode):
+    global _fp32_mode
+    if mode not in ("exact", "bf16"):
+        raise ValueError("fp32 mode must be 'exact' or 'bf16'")
+    prev, _fp32_mode = _fp32_mode, mode
+    return prev
+
+
+def force_path(path):
+    global _force_path
+    prev, _force_path = _force_path, path
+    return prev
+
+
+def choose_jparts(n_rb, nsplit, n_jb, n_sm=148, max_parts=16):
+    """Split the column sweep so that (row blocks x column groups x parts) fills the SMs evenly.
+
+    cost model: rounds of `n_sm` concurrent work items x (tiles per item + 1 tile of prologue/drain).
+    """
+    best, best_cost = 1, None
+    for jp in range(1, max(1, min(n_jb, max_parts)) + 1):
+        rounds = math.ceil(n_rb * nsplit * jp / n_sm)
+        cost = rounds * (math.ceil(n_jb / jp) + 1.0)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = jp, cost
+    return best
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    # ------------------------------------------------------------------ tensor plumbing
+    def prep(self, x):
+        if not isinstance(x, torch.Tensor) or x.dim() != 2:
+            raise ValueError("expected a 2-D [B, D] tensor")
+        if not x.is_cuda:
+            raise RuntimeError("sparsify_clip_b200 runs on CUDA tensors only (no CPU fallback)")
+        x = x.detach()
+        if x.dtype not in _DT:
+            x = x.float()
+        if x.dtype == torch.float32 and _fp32_mode == "bf16":
+            x = x.to(torch.bfloat16)
+        if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
+            x = x.contiguous()
+        return x
+
+    def path_for(self, *mats):
+        if _force_path is not None:
+            return _force_path
+        for m in mats:
+            if m.dtype == torch.float32 or m.shape[1] % 8 or m.stride(0) % 8 or m.data_ptr() % 16:
+                return PATH_SIMT
+        return PATH_TC
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _n_sm(self, dev):
+        return torch.cuda.get_device_properties(dev).multi_processor_count
+
+    def _jparts(self, path, nA, nB, D, grad, dev):
+        if path == PATH_TC:
+            kch = (D + 63) // 64
+            return choose_jparts((nA + 127) // 128, (kch + 3) // 4 if grad else 1, (nB + 127) // 128, self._n_sm(dev))
+        tiles = ((nA + 31) // 32) * (((D + 127) // 128) if grad else 1)
+        return max(1, min((nB + 31) // 32, (2 * self._n_sm(dev)) // max(tiles, 1)))
+
+    def sum(self, x):
+        x = x.contiguous().view(-1)
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        scratch = torch.empty(1024, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(self.lib.scb_sum(_ptr(x), x.numel(), _ptr(scratch), _ptr(out), self._stream()), "sum")
+        return out
+
+    # ------------------------------------------------------------------ row-wise
+    def row_sqnorm(self, x):
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(self.lib.scb_row_sqnorm(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _DT[x.dtype], _ptr(out),
+                                          self._stream()), "row_sqnorm")
+        return out
+
+    def row_dot(self, a, b):
+        out = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            check(self.lib.scb_row_dot(_ptr(a), _ptr(b), a.shape[0], a.shape[1], a.stride(0), b.stride(0), _DT[a.dtype],
+                                       _ptr(out), self._stream()), "row_dot")
+        return out
+
+    def lalign_rows(self, x, y):
+        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(self.lib.scb_lalign_rows(_ptr(x), _ptr(y), x.shape[0], x.shape[1], x.stride(0), y.stride(0),
+                                           _DT[x.dtype], _ptr(out), self._stream()), "lalign_rows")
+        return out
+
+    def lalign_bwd(self, x, y, host_scale, dev_scale, want_x=True, want_y=True):
+        n, D = x.shape
+        dX = torch.empty(n, D, dtype=torch.float32, device=x.device) if want_x else None
+        dY = torch.empty(n, D, dtype=torch.float32, device=x.device) if want_y else None
+        with torch.cuda.device(x.device):
+            check(self.lib.scb_lalign_bwd(_ptr(x), _ptr(y), n, D, x.stride(0), y.stride(0), _DT[x.dtype], host_scale,
+                                          _ptr(dev_scale), 0, _ptr(dX), _ptr(dY), self._stream()), "lalign_bwd")
+        return dX, dY
+
+    def centroid_fwd(self, a, b, out_dtype):
+        n, D = a.shape
+        C = torch.empty(n, D, dtype=out_dtype, device=a.device)
+        inv = torch.empty(n, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            check(self.lib.scb_centroid_fwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(C),
+                                            _DT[out_dtype], _ptr(inv), self._stream()), "centroid_fwd")
+        return C, inv
+
+    def centroid_bwd(self, a, b, dC, inv, host_scale=1.0, dev_scale=None):
+        n, D = a.shape
+        dA = torch.empty(n, D, dtype=torch.float32, device=a.device)
+        dB = torch.empty(n, D, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            check(self.lib.scb_centroid_bwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(dC),
+                                            _ptr(inv), host_scale, _ptr(dev_scale), 0, _ptr(dA), _ptr(dB),
+                                            self._stream()), "centroid_bwd")
+        return dA, dB
+
+    def normalize_fwd(self, x, out_dtype):
+        n, D = x.shape
+        Y = torch.empty(n, D, dtype=out_dtype, device=x.device)
+        inv = torch.empty(n, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(self.lib.scb_normalize_fwd(_ptr(x), n, D, x.stride(0), _DT[x.dtype], _ptr(Y), _DT[out_dtype],
+                                             _ptr(inv), self._stream()), "normalize_fwd")
+        return Y, inv
+
+    def normalize_bwd(self, x, dY, inv):
+        n, D = x.shape
+        dX = torch.empty(n, D, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(self.lib.scb_normalize_bwd(_ptr(x), n, D, x.stride(0), _DT[x.dtype], _ptr(dY), _ptr(inv), _ptr(dX),
+                                             self._stream()), "normalize_bwd")
+        return dX
+
+    # ------------------------------------------------------------------ B x B passes
+    def lse(self, A, Ball, scale):
+        """Natural-log row LSE of scale * A @ Ball^T -> [nA] fp32."""
+        nA, D = A.shape
+        nB = Ball.shape[0]
+        path = self.path_for(A, Ball)
+        jp = self._jparts(path, nA, nB, D, False, A.device)
+        nsub = self.lib.scb_pass_nsub(path)
+        pm = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device)
+        pl = torch.empty_like(pm)
+        out = torch.empty(nA, dtype=torch.float32, device=A.device)
+        with torch.cuda.device(A.device):
+            check(self.lib.scb_lse_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0), _DT[A.dtype],
+                                        float(scale), jp, _ptr(pm), _ptr(pl), path, self._stream()), "lse_pass")
+            check(self.lib.scb_lse_combine(_ptr(pm), _ptr(pl), jp * nsub, nA, _ptr(out), self._stream()), "lse_combine")
+        return out
+
+    def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off,
+                    host_scale, dev_scale, want_ws):
+        """dA = s * [ sum_j (P_ij + Q_ij) Ball_j  (j != diagonal)  +  (P_ii + Q_ii - 2) V_i ]  (fp32 [nA, D]);
+        ws = sum_ij (P+Q)_ij (A_i . Ball_j) as a 0-dim tensor (for d/dtau) when want_ws."""
+        nA, D = A.shape
+        nB = Ball.shape[0]
+        path = self.path_for(A, Ball)
+        jp = self._jparts(path, nA, nB, D, True, A.device)
+        nsub = self.lib.scb_pass_nsub(path)
+        out = torch.empty(jp, nA, D, dtype=torch.float32, device=A.device)
+        ws = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
+        dA = torch.empty(nA, D, dtype=torch.float32, device=A.device)
+        with torch.cuda.device(A.device):
+            check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0), _DT[A.dtype],
+                                                float(scale), _ptr(row_lse), _ptr(col_lse_all), int(diag_off), jp,
+                                                _ptr(out), _ptr(ws), path, self._stream()), "anchor_grad_pass")
+            check(self.lib.scb_anchor_grad_finalize(_ptr(out), jp, nA, D, _ptr(V_rows), V_rows.stride(0), _DT[V_rows.dtype],
+                                                    _ptr(row_lse), _ptr(col_lse_rows), _ptr(diag), float(scale),
+                                                    float(host_scale), _ptr(dev_scale), 0, _ptr(dA), self._stream()),
+                  "anchor_grad_finalize")
+        return dA, (self.sum(ws) if want_ws else None)
+
+    def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None):
+        """One sweep over the pairwise Gaussian potentials of the rows of Xr against Xall.
+        Returns {'rs_sum': 0-dim sum_i sum_{j != i} w_ij, and, when need_grad, 'U', 'rq', ...}."""
+        nR, D = Xr.shape
+        nAll = Xall.shape[0]
+        path = self.path_for(Xr, Xall)
+        jp = self._jparts(path, nR, nAll, D, need_grad, Xr.device)
+        nsub = self.lib.scb_pass_nsub(path)
+        if sqn_all is None:
+            sqn_all = self.row_sqnorm(Xall)
+        if sqn_r is None:  # by contract Xr holds rows [row_offset, row_offset + nR) of Xall
+            sqn_r = sqn_all[row_offset:row_offset + nR]
+        rs = torch.empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
+        core = {"jparts": jp, "nparts": jp * nsub, "path": path}
+        with torch.cuda.device(Xr.device):
+            if need_grad:
+                U = torch.empty(jp, nR, D, dtype=torch.float32, device=Xr.device)
+                rq = torch.empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
+                check(self.lib.scb_lunif_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0), _DT[Xr.dtype],
+                                              float(t), _ptr(sqn_r), _ptr(sqn_all), int(row_offset), jp, _ptr(U), _ptr(rq),
+                                              _ptr(rs), path, self._stream()), "lunif_pass")
+                core.update(U=U, rq=rq)
+            else:
+                check(self.lib.scb_lunif_sum_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),
+                                                  _DT[Xr.dtype], float(t), _ptr(sqn_r), _ptr(sqn_all), int(row_offset), jp,
+                                                  _ptr(rs), path, self._stream()), "lunif_sum_pass")
+        core["rs_sum"] = self.sum(rs)
+        return core
+
+    def lunif_grad(self, core, Xr, host_scale, dev_scale):
+        """dX = s * (rq_i x_i - U_i), s = host_scale * dev_scale (0-dim device tensor)."""
+        nR, D = Xr.shape
+        dX = torch.empty(nR, D, dtype=torch.float32, device=Xr.device)
+        with torch.cuda.device(Xr.device):
+            check(self.lib.scb_lunif_grad_finalize(_ptr(core["U"]), core["jparts"], _ptr(core["rq"]), core["nparts"], nR, D,
+                                                   _ptr(Xr), Xr.stride(0), _DT[Xr.dtype], float(host_scale), _ptr(dev_scale),
+                                                   0, _ptr(dX), self._stream()), "lunif_grad_finalize")
+        return dX
+
+    def sparsify_sum(self, Xr, Xall, row_offset):
+        nR, D = Xr.shape
+        nAll = Xall.shape[0]
+        path = self.path_for(Xr, Xall)
+        jp = self._jparts(path, nR, nAll, D, False, Xr.device)
+        nsub = self.lib.scb_pass_nsub(path)
+        rs = torch.empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
+        with torch.cuda.device(Xr.device):
+            check(self.lib.scb_sparsify_sum_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),
+                                                 _DT[Xr.dtype], int(row_offset), jp, _ptr(rs), path, self._stream()),
+                  "sparsify_sum_pass")
+        return self.sum(rs)
+
+
+_backend = None
+
+
+def get_backend():
+    """The one and only compute backend.  Raises if the CUDA library is unavailable."""
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend(b):
+    """Test hook (tests/ inject an oracle-backed double to exercise the sharding logic on CPU)."""
+    global _backend
+    prev, _backend = _backend, b
+    return prev

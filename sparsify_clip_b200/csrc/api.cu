@@ -1,0 +1,85 @@
+// api.cu -- extern "C" entry points of the B x B passes declared in include/scb200.h:
+// argument validation and dispatch to the SIMT (simt_pass.cu) or tensor-core (tc_pass.cu) path.
+#include "common.cuh"
+
+int scb_simt_lse(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, cudaStream_t);
+int scb_simt_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*,
+                         const float*, int64_t, int, float*, float*, cudaStream_t);
+int scb_simt_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
+                   int64_t, int, float*, float*, float*, cudaStream_t);
+int scb_simt_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
+int scb_tc_lse(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, cudaStream_t);
+int scb_tc_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
+                       int64_t, int, float*, float*, cudaStream_t);
+int scb_tc_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*, int64_t,
+                 int, float*, float*, float*, cudaStream_t);
+int scb_tc_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
+int scb_tc_set_flags(int);
+
+#define SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path)                                           \
+  SCB_CHECK_ARG(scb_dtype_ok(dtype), SCB_E_DTYPE, "%s: unsupported dtype %d", __func__, (int)(dtype));             \
+  SCB_CHECK_ARG((path) == SCB_PATH_SIMT || (path) == SCB_PATH_TC, SCB_E_ARG, "%s: unknown path %d", __func__, (int)(path)); \
+  SCB_CHECK_ARG((nA) >= 0 && (nB) >= 0 && (D) > 0 && (ldA) >= (D) && (ldB) >= (D), SCB_E_ARG,                      \
+                "%s: bad shape nA=%lld nB=%lld D=%d ldA=%lld ldB=%lld", __func__, (long long)(nA), (long long)(nB), \
+                (int)(D), (long long)(ldA), (long long)(ldB));                                                     \
+  SCB_CHECK_ARG(((A) && (Bm)) || (nA) == 0, SCB_E_ARG, "%s: null operand", __func__);                              \
+  SCB_CHECK_ARG((jparts) >= 1, SCB_E_ARG, "%s: jparts must be >= 1", __func__)
+
+extern "C" int scb_pass_nsub(int path) { return path == SCB_PATH_TC ? 2 : 1; }
+extern "C" int scb_set_tc_flags(int flags) { return scb_tc_set_flags(flags); }
+
+extern "C" int scb_lse_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                            float scale, int jparts, float* part_m, float* part_l, int path, void* stream) {
+  SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path);
+  SCB_CHECK_ARG((part_m && part_l) || nA == 0, SCB_E_ARG, "lse_pass: null output");
+  SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "lse_pass: needs scale > 0 and nB > 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  return path == SCB_PATH_TC ? scb_tc_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, s)
+                             : scb_simt_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, s);
+}
+
+extern "C" int scb_anchor_grad_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
+                                    int dtype, float scale, const float* row_lse, const float* col_lse, int64_t diag_off,
+                                    int jparts, float* out, float* ws, int path, void* stream) {
+  SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path);
+  SCB_CHECK_ARG((row_lse && col_lse && out) || nA == 0, SCB_E_ARG, "anchor_grad_pass: null argument");
+  SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "anchor_grad_pass: needs scale > 0 and nB > 0");
+  cudaStream_t s = (cudaStream_t)stream;
+  return path == SCB_PATH_TC
+             ? scb_tc_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s)
+             : scb_simt_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s);
+}
+
+extern "C" int scb_lunif_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
+                              int dtype, float t, const float* sqn_r, const float* sqn_all, int64_t row_offset, int jparts,
+                              float* U, float* rq, float* rs, int path, void* stream) {
+  SCB_PASS_CHECKS(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, jparts, path);
+  SCB_CHECK_ARG((sqn_r && sqn_all && U && rq && rs) || nR == 0, SCB_E_ARG, "lunif_pass: null argument");
+  SCB_CHECK_ARG(nAll > 0, SCB_E_ARG, "lunif_pass: empty column side");
+  cudaStream_t s = (cudaStream_t)stream;
+  return path == SCB_PATH_TC
+             ? scb_tc_lunif(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, t, sqn_r, sqn_all, row_offset, jparts, U, rq, rs, s)
+             : scb_simt_lunif(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, t, sqn_r, sqn_all, row_offset, jparts, U, rq, rs, s);
+}
+
+extern "C" int scb_lunif_sum_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
+                                  int dtype, float t, const float* sqn_r, const float* sqn_all, int64_t row_offset, int jparts,
+                                  float* rs, int path, void* stream) {
+  SCB_PASS_CHECKS(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, jparts, path);
+  SCB_CHECK_ARG((sqn_r && sqn_all && rs) || nR == 0, SCB_E_ARG, "lunif_sum_pass: null argument");
+  SCB_CHECK_ARG(nAll > 0, SCB_E_ARG, "lunif_sum_pass: empty column side");
+  cudaStream_t s = (cudaStream_t)stream;
+  return path == SCB_PATH_TC
+             ? scb_tc_lunif(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, t, sqn_r, sqn_all, row_offset, jparts, nullptr, nullptr, rs, s)
+             : scb_simt_lunif(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, t, sqn_r, sqn_all, row_offset, jparts, nullptr, nullptr, rs, s);
+}
+
+extern "C" int scb_sparsify_sum_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
+                                     int dtype, int64_t row_offset, int jparts, float* rs, int path, void* stream) {
+  SCB_PASS_CHECKS(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, jparts, path);
+  SCB_CHECK_ARG(rs || nR == 0, SCB_E_ARG, "sparsify_sum_pass: null output");
+  SCB_CHECK_ARG(nAll > 0, SCB_E_ARG, "sparsify_sum_pass: empty column side");
+  cudaStream_t s = (cudaStream_t)stream;
+  return path == SCB_PATH_TC ? scb_tc_sparsify_sum(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, row_offset, jparts, rs, s)
+                             : scb_simt_sparsify_sum(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, row_offset, jparts, rs, s);
+}

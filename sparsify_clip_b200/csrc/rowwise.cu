@@ -1,0 +1,416 @@
+// rowwise.cu -- O(B*D) kernels of the loss path: norms, diagonal logits, L_align, centroids,
+// normalise, deterministic sums and the per-term gradient finalisers.  One warp per row,
+// 16-byte vector loads when the layout allows (VEC), scalar otherwise.  HBM-bound; each
+// input row is read exactly once per kernel.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+void scb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* scb_last_error(void) { return g_err; }
+extern "C" int scb_version(void) { return 100; }
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+inline dim3 row_grid(int64_t n) { return dim3((unsigned)((n + kWarpsPerBlock - 1) / kWarpsPerBlock)); }
+
+inline bool vec_ok(const void* p, int64_t ld, int D) { return scb_aligned16(p) && (ld % 8 == 0) && (D % 8 == 0); }
+
+__device__ __forceinline__ float eff_scale(float host_scale, const float* dev_scale) {
+  return dev_scale ? host_scale * __ldg(dev_scale) : host_scale;
+}
+
+// Generic per-row visitor: calls f(d, a[8], b[8], nvalid) over the row in a warp-strided fashion.
+template <bool VEC, bool TWO, class F>
+__device__ __forceinline__ void for_row(const void* A, int64_t ldA, const void* B, int64_t ldB, int dtype,
+                                        int64_t row, int D, int lane, F f) {
+  if (VEC) {
+    for (int d = lane * 8; d < D; d += 256) {
+      float a[8], b[8];
+      scb_ld8(A, dtype, row * ldA + d, a);
+      if (TWO) scb_ld8(B, dtype, row * ldB + d, b);
+      f(d, a, b, 8);
+    }
+  } else {
+    for (int d = lane; d < D; d += 32) {
+      float a[8], b[8];
+      a[0] = scb_ld(A, dtype, row * ldA + d);
+      b[0] = TWO ? scb_ld(B, dtype, row * ldB + d) : 0.f;
+      f(d, a, b, 1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ reductions per row
+// MODE 0: sum a^2 ; 1: sum a*b ; 2: sum (a-b)^2
+template <bool VEC, int MODE>
+__global__ void __launch_bounds__(kThreads) k_row_reduce(const void* __restrict__ A, const void* __restrict__ B,
+                                                         int64_t n, int D, int64_t ldA, int64_t ldB, int dtype,
+                                                         float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float acc = 0.f;
+  for_row<VEC, MODE != 0>(A, ldA, B, ldB, dtype, row, D, lane, [&](int, float(&a)[8], float(&b)[8], int nv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        if (MODE == 0) acc = fmaf(a[i], a[i], acc);
+        if (MODE == 1) acc = fmaf(a[i], b[i], acc);
+        if (MODE == 2) { float t = a[i] - b[i]; acc = fmaf(t, t, acc); }
+      }
+  });
+  acc = scb_warp_sum(acc);
+  if (lane == 0) out[row] = acc;
+}
+
+template <int MODE>
+int launch_row_reduce(const void* A, const void* B, int64_t n, int D, int64_t ldA, int64_t ldB, int dtype, float* out,
+                      cudaStream_t s) {
+  if (n == 0) return 0;
+  bool v = vec_ok(A, ldA, D) && (MODE == 0 || vec_ok(B, ldB, D));
+  if (v) k_row_reduce<true, MODE><<<row_grid(n), kThreads, 0, s>>>(A, B, n, D, ldA, ldB, dtype, out);
+  else k_row_reduce<false, MODE><<<row_grid(n), kThreads, 0, s>>>(A, B, n, D, ldA, ldB, dtype, out);
+  SCB_CHECK_LAUNCH("row_reduce");
+  return 0;
+}
+
+// ------------------------------------------------------------------ L_align backward
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_lalign_bwd(const void* __restrict__ X, const void* __restrict__ Y,
+                                                         int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
+                                                         float host_scale, const float* __restrict__ dev_scale,
+                                                         int accumulate, float* __restrict__ dX, float* __restrict__ dY) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float s = eff_scale(host_scale, dev_scale);
+  for_row<VEC, true>(X, ldX, Y, ldY, dtype, row, D, lane, [&](int d, float(&a)[8], float(&b)[8], int nv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const float g = s * (a[i] - b[i]);
+        const int64_t o = row * (int64_t)D + d + i;
+        if (dX) dX[o] = accumulate ? dX[o] + g : g;
+        if (dY) dY[o] = accumulate ? dY[o] - g : -g;
+      }
+  });
+}
+
+// ------------------------------------------------------------------ centroid / normalise forward
+// CENT: m = (a+b)/2 with eps clamp 1e-12 (F.normalize); else m = a, no eps (x / x.norm()).
+template <bool VEC, bool CENT>
+__global__ void __launch_bounds__(kThreads) k_unit_fwd(const void* __restrict__ A, const void* __restrict__ B, int64_t n,
+                                                       int D, int64_t ldA, int64_t ldB, int dtype, void* __restrict__ C,
+                                                       int out_dtype, float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float acc = 0.f;
+  for_row<VEC, CENT>(A, ldA, B, ldB, dtype, row, D, lane, [&](int, float(&a)[8], float(&b)[8], int nv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) { float m = CENT ? 0.5f * (a[i] + b[i]) : a[i]; acc = fmaf(m, m, acc); }
+  });
+  acc = scb_warp_sum(acc);
+  const float nrm = sqrtf(acc);
+  const float inv = CENT ? 1.f / fmaxf(nrm, 1e-12f) : 1.f / nrm;
+  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+  for_row<VEC, CENT>(A, ldA, B, ldB, dtype, row, D, lane, [&](int d, float(&a)[8], float(&b)[8], int nv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) { float m = CENT ? 0.5f * (a[i] + b[i]) : a[i]; scb_st(C, out_dtype, row * (int64_t)D + d + i, m * inv); }
+  });
+}
+
+// backward of c = m * inv:  dm = (g - c (c.g)) * inv ;  CENT: dA,dB (+)= s*dm/2 ; else dA = dm
+template <bool VEC, bool CENT>
+__global__ void __launch_bounds__(kThreads) k_unit_bwd(const void* __restrict__ A, const void* __restrict__ B, int64_t n,
+                                                       int D, int64_t ldA, int64_t ldB, int dtype,
+                                                       const float* __restrict__ dC, const float* __restrict__ inv_norm,
+                                                       float host_scale, const float* __restrict__ dev_scale,
+                                                       int accumulate, float* __restrict__ dA, float* __restrict__ dB) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float inv = inv_norm[row];
+  float dot = 0.f;
+  for_row<VEC, CENT>(A, ldA, B, ldB, dtype, row, D, lane, [&](int d, float(&a)[8], float(&b)[8], int nv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        float c = (CENT ? 0.5f * (a[i] + b[i]) : a[i]) * inv;
+        dot = fmaf(c, dC[row * (int64_t)D + d + i], dot);
+      }
+  });
+  dot = scb_warp_sum(dot);
+  const float s = eff_scale(host_scale, dev_scale) * (CENT ? 0.5f : 1.f) * inv;
+  for_row<VEC, CENT>(A, ldA, B, ldB, dtype, row, D, lane, [&](int d, float(&a)[8], float(&b)[8], int nv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const int64_t o = row * (int64_t)D + d + i;
+        float c = (CENT ? 0.5f * (a[i] + b[i]) : a[i]) * inv;
+        float g = s * (dC[o] - c * dot);
+        if (dA) dA[o] = accumulate ? dA[o] + g : g;
+        if (CENT && dB) dB[o] = accumulate ? dB[o] + g : g;
+      }
+  });
+}
+
+// ------------------------------------------------------------------ deterministic sum
+constexpr int kSumBlocks = 1024;
+__global__ void __launch_bounds__(256) k_sum_stage1(const float* __restrict__ x, int64_t n, float* __restrict__ scratch) {
+  // contiguous chunk per block, fixed strided order inside -> bitwise reproducible
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = min(lo + per, n);
+  float acc = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) acc += x[i];
+  __shared__ float sm[8];
+  acc = scb_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    scratch[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) k_sum_stage2(const float* __restrict__ scratch, int nb, float* __restrict__ out) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nb; i += 256) acc += scratch[i];
+  __shared__ float sm[8];
+  acc = scb_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i];
+    out[0] = t;
+  }
+}
+
+// ------------------------------------------------------------------ LSE combine
+__global__ void __launch_bounds__(256) k_lse_combine(const float* __restrict__ pm, const float* __restrict__ pl, int nparts,
+                                                     int64_t n, float* __restrict__ lse) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float M = -INFINITY;
+  for (int p = 0; p < nparts; ++p) M = fmaxf(M, pm[(int64_t)p * n + i]);
+  float L = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    const float m = pm[(int64_t)p * n + i];
+    if (m != -INFINITY) L += pl[(int64_t)p * n + i] * exp2f(m - M);
+  }
+  lse[i] = (M + log2f(L)) * SCB_LN2;   // log2 domain -> natural log
+}
+
+// ------------------------------------------------------------------ gradient finalisers
+// dA[i,:] (+)= s * ( sum_p out[p][i,:] + dcoef_i * V[i,:] )
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_anchor_fin(const float* __restrict__ out, int jparts, int64_t n, int D,
+                                                         const void* __restrict__ V, int64_t ldV, int dtype,
+                                                         const float* __restrict__ row_lse,
+                                                         const float* __restrict__ col_lse_rows,
+                                                         const float* __restrict__ diag, float scale, float host_scale,
+                                                         const float* __restrict__ dev_scale, int accumulate,
+                                                         float* __restrict__ dA) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float s = eff_scale(host_scale, dev_scale);
+  const float sii = scale * diag[row];
+  const float dcoef = expf(sii - row_lse[row]) + expf(sii - col_lse_rows[row]) - 2.f;
+  for_row<VEC, false>(V, ldV, nullptr, 0, dtype, row, D, lane, [&](int d, float(&a)[8], float(&)[8], int nv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const int64_t o = row * (int64_t)D + d + i;
+        float acc = 0.f;
+        for (int p = 0; p < jparts; ++p) acc += out[(int64_t)p * n * D + o];
+        const float g = s * fmaf(dcoef, a[i], acc);
+        dA[o] = accumulate ? dA[o] + g : g;
+      }
+  });
+}
+
+// dX[i,:] (+)= s * ( rq_i * x_i - sum_p U[p][i,:] )
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) k_lunif_fin(const float* __restrict__ U, int jparts,
+                                                        const float* __restrict__ rq, int nparts_rq, int64_t n, int D,
+                                                        const void* __restrict__ X, int64_t ld, int dtype,
+                                                        float host_scale, const float* __restrict__ dev_scale,
+                                                        int accumulate, float* __restrict__ dX) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float s = eff_scale(host_scale, dev_scale);
+  float r = 0.f;
+  for (int p = 0; p < nparts_rq; ++p) r += rq[(int64_t)p * n + row];
+  for_row<VEC, false>(X, ld, nullptr, 0, dtype, row, D, lane, [&](int d, float(&a)[8], float(&)[8], int nv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nv) {
+        const int64_t o = row * (int64_t)D + d + i;
+        float acc = 0.f;
+        for (int p = 0; p < jparts; ++p) acc += U[(int64_t)p * n * D + o];
+        const float g = s * fmaf(r, a[i], -acc);
+        dX[o] = accumulate ? dX[o] + g : g;
+      }
+  });
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+#define SCB_COMMON_CHECKS(ptr_ok, n, D, dtype)                                           \
+  SCB_CHECK_ARG(scb_dtype_ok(dtype), SCB_E_DTYPE, "%s: unsupported dtype %d", __func__, (int)(dtype)); \
+  SCB_CHECK_ARG((n) >= 0 && (D) > 0, SCB_E_ARG, "%s: bad shape n=%lld D=%d", __func__, (long long)(n), (int)(D)); \
+  SCB_CHECK_ARG((ptr_ok) || (n) == 0, SCB_E_ARG, "%s: null pointer", __func__)
+
+extern "C" int scb_row_sqnorm(const void* X, int64_t n, int D, int64_t ld, int dtype, float* out, void* stream) {
+  SCB_COMMON_CHECKS(X && out, n, D, dtype);
+  return launch_row_reduce<0>(X, nullptr, n, D, ld, 0, dtype, out, (cudaStream_t)stream);
+}
+
+extern "C" int scb_row_dot(const void* A, const void* B, int64_t n, int D, int64_t ldA, int64_t ldB, int dtype, float* out,
+                           void* stream) {
+  SCB_COMMON_CHECKS(A && B && out, n, D, dtype);
+  return launch_row_reduce<1>(A, B, n, D, ldA, ldB, dtype, out, (cudaStream_t)stream);
+}
+
+extern "C" int scb_lalign_rows(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
+                               float* row_out, void* stream) {
+  SCB_COMMON_CHECKS(X && Y && row_out, n, D, dtype);
+  return launch_row_reduce<2>(X, Y, n, D, ldX, ldY, dtype, row_out, (cudaStream_t)stream);
+}
+
+extern "C" int scb_lalign_bwd(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
+                              float host_scale, const float* dev_scale, int accumulate, float* dX, float* dY, void* stream) {
+  SCB_COMMON_CHECKS(X && Y && (dX || dY), n, D, dtype);
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok(X, ldX, D) && vec_ok(Y, ldY, D))
+    k_lalign_bwd<true><<<row_grid(n), kThreads, 0, s>>>(X, Y, n, D, ldX, ldY, dtype, host_scale, dev_scale, accumulate, dX, dY);
+  else
+    k_lalign_bwd<false><<<row_grid(n), kThreads, 0, s>>>(X, Y, n, D, ldX, ldY, dtype, host_scale, dev_scale, accumulate, dX, dY);
+  SCB_CHECK_LAUNCH("lalign_bwd");
+  return 0;
+}
+
+extern "C" int scb_centroid_fwd(const void* A, const void* B, int64_t n, int D, int64_t ldA, int64_t ldB, int dtype, void* C_out,
+                                int out_dtype, float* inv_norm, void* stream) {
+  SCB_COMMON_CHECKS(A && B && C_out, n, D, dtype);
+  SCB_CHECK_ARG(scb_dtype_ok(out_dtype), SCB_E_DTYPE, "centroid_fwd: bad out dtype");
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok(A, ldA, D) && vec_ok(B, ldB, D))
+    k_unit_fwd<true, true><<<row_grid(n), kThreads, 0, s>>>(A, B, n, D, ldA, ldB, dtype, C_out, out_dtype, inv_norm);
+  else
+    k_unit_fwd<false, true><<<row_grid(n), kThreads, 0, s>>>(A, B, n, D, ldA, ldB, dtype, C_out, out_dtype, inv_norm);
+  SCB_CHECK_LAUNCH("centroid_fwd");
+  return 0;
+}
+
+extern "C" int scb_centroid_bwd(const void* A, const void* B, int64_t n, int D, int64_t ldA, int64_t ldB, int dtype,
+                                const float* dC, const float* inv_norm, float host_scale, const float* dev_scale,
+                                int accumulate, float* dA, float* dB, void* stream) {
+  SCB_COMMON_CHECKS(A && B && dC && inv_norm && (dA || dB), n, D, dtype);
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok(A, ldA, D) && vec_ok(B, ldB, D))
+    k_unit_bwd<true, true><<<row_grid(n), kThreads, 0, s>>>(A, B, n, D, ldA, ldB, dtype, dC, inv_norm, host_scale, dev_scale, accumulate, dA, dB);
+  else
+    k_unit_bwd<false, true><<<row_grid(n), kThreads, 0, s>>>(A, B, n, D, ldA, ldB, dtype, dC, inv_norm, host_scale, dev_scale, accumulate, dA, dB);
+  SCB_CHECK_LAUNCH("centroid_bwd");
+  return 0;
+}
+
+extern "C" int scb_normalize_fwd(const void* X, int64_t n, int D, int64_t ld, int dtype, void* Y, int out_dtype, float* inv_norm,
+                                 void* stream) {
+  SCB_COMMON_CHECKS(X && Y, n, D, dtype);
+  SCB_CHECK_ARG(scb_dtype_ok(out_dtype), SCB_E_DTYPE, "normalize_fwd: bad out dtype");
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok(X, ld, D))
+    k_unit_fwd<true, false><<<row_grid(n), kThreads, 0, s>>>(X, nullptr, n, D, ld, 0, dtype, Y, out_dtype, inv_norm);
+  else
+    k_unit_fwd<false, false><<<row_grid(n), kThreads, 0, s>>>(X, nullptr, n, D, ld, 0, dtype, Y, out_dtype, inv_norm);
+  SCB_CHECK_LAUNCH("normalize_fwd");
+  return 0;
+}
+
+extern "C" int scb_normalize_bwd(const void* X, int64_t n, int D, int64_t ld, int dtype, const float* dY, const float* inv_norm,
+                                 float* dX, void* stream) {
+  SCB_COMMON_CHECKS(X && dY && inv_norm && dX, n, D, dtype);
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok(X, ld, D))
+    k_unit_bwd<true, false><<<row_grid(n), kThreads, 0, s>>>(X, nullptr, n, D, ld, 0, dtype, dY, inv_norm, 1.f, nullptr, 0, dX, nullptr);
+  else
+    k_unit_bwd<false, false><<<row_grid(n), kThreads, 0, s>>>(X, nullptr, n, D, ld, 0, dtype, dY, inv_norm, 1.f, nullptr, 0, dX, nullptr);
+  SCB_CHECK_LAUNCH("normalize_bwd");
+  return 0;
+}
+
+extern "C" int scb_sum(const float* x, int64_t n, float* scratch, float* out, void* stream) {
+  SCB_CHECK_ARG(x && scratch && out && n >= 0, SCB_E_ARG, "scb_sum: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int nb = (int)((n + 4095) / 4096);
+  if (nb < 1) nb = 1;
+  if (nb > kSumBlocks) nb = kSumBlocks;
+  k_sum_stage1<<<nb, 256, 0, s>>>(x, n, scratch);
+  k_sum_stage2<<<1, 256, 0, s>>>(scratch, nb, out);
+  SCB_CHECK_LAUNCH("scb_sum");
+  return 0;
+}
+
+extern "C" int scb_lse_combine(const float* part_m, const float* part_l, int nparts, int64_t n, float* lse, void* stream) {
+  SCB_CHECK_ARG(part_m && part_l && lse && nparts > 0 && n >= 0, SCB_E_ARG, "lse_combine: bad argument");
+  if (n == 0) return 0;
+  k_lse_combine<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part_m, part_l, nparts, n, lse);
+  SCB_CHECK_LAUNCH("lse_combine");
+  return 0;
+}
+
+extern "C" int scb_anchor_grad_finalize(const float* out, int jparts, int64_t n, int D, const void* V, int64_t ldV, int dtype,
+                                        const float* row_lse, const float* col_lse_rows, const float* diag, float scale,
+                                        float host_scale, const float* dev_scale, int accumulate, float* dA, void* stream) {
+  SCB_COMMON_CHECKS(out && V && row_lse && col_lse_rows && diag && dA, n, D, dtype);
+  SCB_CHECK_ARG(jparts > 0, SCB_E_ARG, "anchor_grad_finalize: jparts");
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok(V, ldV, D))
+    k_anchor_fin<true><<<row_grid(n), kThreads, 0, s>>>(out, jparts, n, D, V, ldV, dtype, row_lse, col_lse_rows, diag, scale, host_scale, dev_scale, accumulate, dA);
+  else
+    k_anchor_fin<false><<<row_grid(n), kThreads, 0, s>>>(out, jparts, n, D, V, ldV, dtype, row_lse, col_lse_rows, diag, scale, host_scale, dev_scale, accumulate, dA);
+  SCB_CHECK_LAUNCH("anchor_grad_finalize");
+  return 0;
+}
+
+extern "C" int scb_lunif_grad_finalize(const float* U, int jparts, const float* rq, int nparts_rq, int64_t n, int D, const void* X,
+                                       int64_t ld, int dtype, float host_scale, const float* dev_scale, int accumulate,
+                                       float* dX, void* stream) {
+  SCB_COMMON_CHECKS(U && rq && X && dX, n, D, dtype);
+  SCB_CHECK_ARG(jparts > 0 && nparts_rq > 0, SCB_E_ARG, "lunif_grad_finalize: parts");
+  if (n == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (vec_ok(X, ld, D))
+    k_lunif_fin<true><<<row_grid(n), kThreads, 0, s>>>(U, jparts, rq, nparts_rq, n, D, X, ld, dtype, host_scale, dev_scale, accumulate, dX);
+  else
+    k_lunif_fin<false><<<row_grid(n), kThreads, 0, s>>>(U, jparts, rq, nparts_rq, n, D, X, ld, dtype, host_scale, dev_scale, accumulate, dX);
+  SCB_CHECK_LAUNCH("lunif_grad_finalize");
+  return 0;
+}

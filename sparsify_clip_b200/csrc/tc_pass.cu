@@ -1,0 +1,575 @@
+// tc_pass.cu -- SCB_PATH_TC: the B x B passes on the 5th-gen tensor cores (sm_100a).
+//
+// One persistent, warp-specialised CTA per SM (384 threads, 1 CTA/SM):
+//   warp 0      TMA producer   cp.async.bulk.tensor 2D loads of [128 rows x 64 cols] 16-bit tiles
+//                              (128B swizzle) into a ring of 16 KB shared-memory slots
+//   warp 1      MMA issuer     one lane issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM)
+//   warp 2      TMEM allocator (all 512 columns; 1 CTA per SM by construction)
+//   warps 4-11  epilogue       tcgen05.ld S tile -> exp2 / online LSE / masks in registers ->
+//                              16-bit weight tile (shared memory, or TMEM for the TS-mode MMA)
+//
+// A work item is (row block of 128 rows of A, output column group of <=256 columns, column part).
+// For every 128-column block j of the sweep:
+//   MMA1   S[128x128]   = A_rb . Bm_j^T          (K = D, both operands K-major, A stationary in smem
+//                                                  when D <= 512, streamed otherwise)
+//   epi    W[128x128]   = f(S)                    (mode-specific, never leaves the SM)
+//   MMA2   OUT[128xN2] += W . Bm_j[:, group]      (K = 128; W is the K-major A operand, the SAME
+//                                                  Bm tile layout is re-read as an MN-major B operand)
+// MMA1 of tile t+1 is issued before MMA2 of tile t, so the tensor pipe works on the next S tile
+// while the epilogue warps transform the current one (S is double-buffered in TMEM).
+// TMEM columns: OUT [0,256) | S0 [256,384) | S1 [384,512).
+//
+// Column-tail / row-tail / D-tail handling relies on TMA zero fill plus masks in the epilogue.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+enum { M_LSE = 0, M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2, M_LUNIF_SUM = 3, M_SPARSIFY_SUM = 4 };
+
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kSlotBytes = 128 * 64 * 2;  // one [128 x 64] 16-bit tile
+constexpr int kMaxStages = 14;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColOut = 0, kColS0 = 256;
+
+struct TcParams {
+  int64_t nA, nB;
+  int D, kch, nsplit, n_rb, n_jb, jparts;
+  int a_stationary, nstage, g_in_tmem, fmt;  // fmt: 1 bf16, 0 fp16
+  float p0;                                  // LSE/anchor: scale*log2e ; lunif: t*log2e
+  const float* rowvec;
+  const float* colvec;
+  int64_t diag_off;
+  float* out;  // [jparts][nA][D]
+  float* s0;   // LSE: part_m ; anchor: ws ; lunif grad: rq ; sums: rs      [jparts*2][nA]
+  float* s1;   // LSE: part_l ; lunif grad: rs
+};
+
+// barrier indices inside the barrier block
+enum {
+  BAR_FULL = 0,                      // [kMaxStages]
+  BAR_EMPTY = kMaxStages,            // [kMaxStages]
+  BAR_A_FULL = 2 * kMaxStages,
+  BAR_A_EMPTY,
+  BAR_S_FULL,                        // [2]
+  BAR_S_EMPTY = BAR_S_FULL + 2,      // [2]
+  BAR_G_FULL = BAR_S_EMPTY + 2,
+  BAR_G_EMPTY,
+  BAR_OUT_FULL,
+  BAR_OUT_EMPTY,
+  BAR_COUNT
+};
+
+struct Ring {
+  uint32_t slot, bits;
+  __device__ __forceinline__ uint32_t take(int n, int nstage) {  // n contiguous slots, never wrapping
+    if (slot + n > (uint32_t)nstage) slot = 0;
+    const uint32_t s = slot;
+    slot += n;
+    if (slot >= (uint32_t)nstage) slot = 0;
+    return s;
+  }
+  __device__ __forceinline__ uint32_t parity_then_flip(uint32_t s) {
+    const uint32_t p = (bits >> s) & 1u;
+    bits ^= (1u << s);
+    return p;
+  }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
+  constexpr bool GRAD = (MODE == M_ANCHOR_GRAD || MODE == M_LUNIF_GRAD);
+  constexpr bool NEED_COLVEC = (MODE == M_ANCHOR_GRAD || MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = P.a_stationary ? (uint32_t)P.kch * kSlotBytes : 0u;
+  const uint32_t sm_a = smem_base;
+  const uint32_t sm_ring = sm_a + a_bytes;
+  const uint32_t sm_g = sm_ring + (uint32_t)P.nstage * kSlotBytes;
+  const uint32_t g_bytes = (GRAD && !P.g_in_tmem) ? 2u * kSlotBytes : 0u;
+  const uint32_t sm_cbuf = sm_g + g_bytes;            // 2 x 128 floats
+  const uint32_t sm_bar = sm_cbuf + 1024u;            // BAR_COUNT x 8 bytes
+  const uint32_t sm_tmem_ptr = sm_bar + BAR_COUNT * 8u;
+  auto bar = [&](int i) -> uint32_t { return sm_bar + 8u * (uint32_t)i; };
+  // generic pointers for the few plain loads/stores
+  uint8_t* gen_base = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  float* cbuf = reinterpret_cast<float*>(gen_base + (sm_cbuf - smem_base));
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sm_tmem_ptr - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsplit_eff = GRAD ? P.nsplit : 1;
+  const int n_items = P.n_rb * nsplit_eff * P.jparts;
+  const uint32_t s_empty_count = (GRAD && P.g_in_tmem) ? 1u : 8u;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kMaxStages; ++i) { ptx::mbar_init(bar(BAR_FULL + i), 1); ptx::mbar_init(bar(BAR_EMPTY + i), 1); }
+    ptx::mbar_init(bar(BAR_A_FULL), 1);
+    ptx::mbar_init(bar(BAR_A_EMPTY), 1);
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(bar(BAR_S_FULL + b), 1); ptx::mbar_init(bar(BAR_S_EMPTY + b), s_empty_count); }
+    ptx::mbar_init(bar(BAR_G_FULL), 8);
+    ptx::mbar_init(bar(BAR_G_EMPTY), 1);
+    ptx::mbar_init(bar(BAR_OUT_FULL), 1);
+    ptx::mbar_init(bar(BAR_OUT_EMPTY), 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(sm_tmem_ptr, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_slot;
+
+  // =========================================================================== TMA producer
+  if (warp == 0) {
+    if (lane == 0) {
+      Ring ring{0u, 0xFFFFFFFFu};
+      uint32_t a_empty_par = 1;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item % nsplit_eff;
+        const int rb = (item / nsplit_eff) % P.n_rb;
+        const int jp = item / (nsplit_eff * P.n_rb);
+        const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
+        const int nt = jb_hi - jb_lo;
+        const int gch = min(4, P.kch - 4 * split);
+        if (P.a_stationary) {
+          ptx::mbar_wait(bar(BAR_A_EMPTY), a_empty_par, 100);
+          a_empty_par ^= 1;
+          ptx::mbar_expect_tx(bar(BAR_A_FULL), (uint32_t)P.kch * kSlotBytes);
+          for (int kc = 0; kc < P.kch; ++kc) ptx::tma_load_2d(sm_a + kc * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_A_FULL));
+        }
+        auto load_b2 = [&](int tt) {
+          const uint32_t s0 = ring.take(gch, P.nstage);
+          for (int c = 0; c < gch; ++c) {
+            const uint32_t s = s0 + c;
+            ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), 110);
+            ptx::mbar_expect_tx(bar(BAR_FULL + s), kSlotBytes);
+            ptx::tma_load_2d(sm_ring + s * kSlotBytes, &tmB, (4 * split + c) * 64, (jb_lo + tt) * 128, bar(BAR_FULL + s));
+          }
+        };
+        for (int t = 0; t < nt; ++t) {
+          for (int kc = 0; kc < P.kch; ++kc) {
+            if (!P.a_stationary) {
+              const uint32_t s = ring.take(1, P.nstage);
+              ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), 120);
+              ptx::mbar_expect_tx(bar(BAR_FULL + s), kSlotBytes);
+              ptx::tma_load_2d(sm_ring + s * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_FULL + s));
+            }
+            const uint32_t s = ring.take(1, P.nstage);
+            ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), 121);
+            ptx::mbar_expect_tx(bar(BAR_FULL + s), kSlotBytes);
+            ptx::tma_load_2d(sm_ring + s * kSlotBytes, &tmB, kc * 64, (jb_lo + t) * 128, bar(BAR_FULL + s));
+          }
+          if (GRAD && t >= 1) load_b2(t - 1);
+        }
+        if (GRAD && nt > 0) load_b2(nt - 1);
+      }
+    }
+  }
+  // =========================================================================== MMA issuer
+  else if (warp == 1) {
+    if (lane == 0) {
+      Ring ring{0u, 0u};
+      uint32_t a_full_par = 0, out_empty_par = 1;
+      uint32_t gt1 = 0, gt2 = 0;  // global tile counters of issued MMA1 / MMA2
+      const uint32_t idesc1 = ptx::idesc_f16(128, 128, P.fmt, 0, 0);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item % nsplit_eff;
+        const int jp = item / (nsplit_eff * P.n_rb);
+        const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
+        const int nt = jb_hi - jb_lo;
+        const int gch = min(4, P.kch - 4 * split);
+        const uint32_t idesc2 = ptx::idesc_f16(128, 64 * gch, P.fmt, 0, 1);
+        if (P.a_stationary) {
+          ptx::mbar_wait(bar(BAR_A_FULL), a_full_par, 200);
+          a_full_par ^= 1;
+        }
+        auto mma1 = [&](bool last) {
+          const uint32_t b = gt1 & 1u;
+          ptx::mbar_wait(bar(BAR_S_EMPTY + b), ((gt1 >> 1) & 1u) ^ 1u, 210);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
+          for (int kc = 0; kc < P.kch; ++kc) {
+            uint32_t a_addr, sa = 0;
+            if (P.a_stationary) {
+              a_addr = sm_a + kc * kSlotBytes;
+            } else {
+              sa = ring.take(1, P.nstage);
+              ptx::mbar_wait(bar(BAR_FULL + sa), ring.parity_then_flip(sa), 211);
+              a_addr = sm_ring + sa * kSlotBytes;
+            }
+            const uint32_t sb = ring.take(1, P.nstage);
+            ptx::mbar_wait(bar(BAR_FULL + sb), ring.parity_then_flip(sb), 212);
+            ptx::tc_fence_after();
+            const uint32_t b_addr = sm_ring + sb * kSlotBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_ss(d_tmem, ptx::desc_kmajor(a_addr + k * 32), ptx::desc_kmajor(b_addr + k * 32), idesc1,
+                           (uint32_t)((kc | k) != 0));
+            if (!P.a_stationary) ptx::umma_commit(bar(BAR_EMPTY + sa));
+            ptx::umma_commit(bar(BAR_EMPTY + sb));
+          }
+          ptx::umma_commit(bar(BAR_S_FULL + b));
+          if (last && P.a_stationary) ptx::umma_commit(bar(BAR_A_EMPTY));
+          ++gt1;
+        };
+        auto mma2 = [&](bool first, bool last) {
+          const uint32_t b = gt2 & 1u;
+          ptx::mbar_wait(bar(BAR_G_FULL), gt2 & 1u, 220);
+          if (first) {
+            ptx::mbar_wait(bar(BAR_OUT_EMPTY), out_empty_par, 221);
+            out_empty_par ^= 1;
+          }
+          const uint32_t s0 = ring.take(gch, P.nstage);
+          for (int c = 0; c < gch; ++c) ptx::mbar_wait(bar(BAR_FULL + s0 + c), ring.parity_then_flip(s0 + c), 222);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + kColOut;
+          const uint32_t v_addr = sm_ring + s0 * kSlotBytes;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t bdesc = ptx::desc_mnmajor(v_addr + ks * 2048, kSlotBytes);
+            const uint32_t accum = (uint32_t)!(first && ks == 0);
+            if (P.g_in_tmem) {
+              const uint32_t a_tmem = tmem_base + kColS0 + 128u * b + (uint32_t)(ks >> 2) * 64u + (uint32_t)(ks & 3) * 8u;
+              ptx::umma_ts(d_tmem, a_tmem, bdesc, idesc2, accum);
+            } else {
+              const uint64_t adesc = ptx::desc_kmajor(sm_g + (uint32_t)(ks >> 2) * kSlotBytes + (uint32_t)(ks & 3) * 32u);
+              ptx::umma_ss(d_tmem, adesc, bdesc, idesc2, accum);
+            }
+          }
+          for (int c = 0; c < gch; ++c) ptx::umma_commit(bar(BAR_EMPTY + s0 + c));
+          if (P.g_in_tmem) ptx::umma_commit(bar(BAR_S_EMPTY + b));
+          else ptx::umma_commit(bar(BAR_G_EMPTY));
+          if (last) ptx::umma_commit(bar(BAR_OUT_FULL));
+          ++gt2;
+        };
+        for (int t = 0; t < nt; ++t) {
+          mma1(t == nt - 1);
+          if (GRAD && t >= 1) mma2(t == 1, false);
+        }
+        if (GRAD && nt > 0) mma2(nt == 1, true);
+      }
+    }
+  }
+  // =========================================================================== epilogue warps
+  else if (warp >= 4) {
+    const int e = warp - 4;
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int h = e >> 2;         // which 64-column half of the S tile
+    const int rrow = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    uint32_t gt = 0, item_cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_cnt) {
+      const int split = item % nsplit_eff;
+      const int rb = (item / nsplit_eff) % P.n_rb;
+      const int jp = item / (nsplit_eff * P.n_rb);
+      const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
+      const int nt = jb_hi - jb_lo;
+      const int gch = min(4, P.kch - 4 * split);
+      const int64_t gi = (int64_t)rb * 128 + rrow;
+      const bool row_ok = gi < P.nA;
+      // per-row constants and running statistics
+      float rowc = 0.f;
+      if (MODE == M_ANCHOR_GRAD) rowc = row_ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
+      if (MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM) rowc = row_ok ? P.rowvec[gi] * P.p0 : 0.f;
+      float st0 = (MODE == M_LSE) ? -INFINITY : 0.f, st1 = 0.f;
+      const int64_t my_diag_col = gi + P.diag_off;  // column index that is "the diagonal" of this row
+
+      for (int t = 0; t < nt; ++t, ++gt) {
+        const uint32_t b = gt & 1u;
+        const int jb = jb_lo + t;
+        const int64_t col0 = (int64_t)jb * 128 + 64 * h;     // first global column handled by this warp
+        const bool tile_partial = ((int64_t)jb * 128 + 128) > P.nB;
+        if (NEED_COLVEC) {
+          const int idx = e * 32 + lane;
+          if (idx < 128) {
+            const int64_t gj = (int64_t)jb * 128 + idx;
+            float cv = INFINITY;
+            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * P.p0;
+            cbuf[b * 128 + idx] = cv;
+          }
+          ptx::named_bar_sync(1, kEpiThreads);
+        }
+        ptx::mbar_wait(bar(BAR_S_FULL + b), (gt >> 1) & 1u, 300);
+        ptx::tc_fence_after();
+        // does the diagonal cross the 32x64 block this warp handles?
+        const int64_t drow0 = (int64_t)rb * 128 + 32 * q + P.diag_off;
+        const bool diag_here = (drow0 < col0 + 64) && (drow0 + 32 > col0);
+
+        uint32_t packed[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b + 64u * h + 32u * cc, v);
+          ptx::tmem_ld_wait();
+          const int64_t cbase = col0 + 32 * cc;
+          const float* cb = cbuf + b * 128 + 64 * h + 32 * cc;
+          if (MODE == M_LSE) {
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float g = __uint_as_float(v[c]);
+              if (tile_partial && (cbase + c) >= P.nB) { g = -INFINITY; v[c] = __float_as_uint(g); }
+              cmax = fmaxf(cmax, g);
+            }
+            if (cmax != -INFINITY) {
+              const float mnew = fmaxf(st0, cmax * P.p0);
+              float sum = 0.f;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) sum += scb_ex2(fmaf(__uint_as_float(v[c]), P.p0, -mnew));
+              st1 = st1 * scb_ex2(st0 - mnew) + sum;
+              st0 = mnew;
+            }
+          } else if (MODE == M_SPARSIFY_SUM) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float g = __uint_as_float(v[c]);
+              const float er = g - ((diag_here && (cbase + c) == my_diag_col) ? 1.f : -1.f);
+              const bool ok = !tile_partial || (cbase + c) < P.nB;
+              st0 += ok ? er * er : 0.f;
+            }
+          } else {
+            float w[32];
+            if (MODE == M_ANCHOR_GRAD) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const float g = __uint_as_float(v[c]);
+                const float y = g * P.p0;
+                float ww = scb_ex2(y - rowc) + scb_ex2(y - cb[c]);
+                if (tile_partial && (cbase + c) >= P.nB) ww = 0.f;
+                st0 = fmaf(ww, g, st0);
+                w[c] = ww;
+              }
+            } else {  // lunif: exp2(2 p0 g - p0 n_i - p0 n_j); invalid columns carry +inf in cb -> 0
+              const float two_p0 = 2.f * P.p0;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) w[c] = scb_ex2(fmaf(__uint_as_float(v[c]), two_p0, -(rowc + cb[c])));
+            }
+            if (diag_here) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if ((cbase + c) == my_diag_col) w[c] = 0.f;
+            }
+            if (MODE == M_LUNIF_SUM) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) st1 += w[c];
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const uint32_t pk = P.fmt ? ptx::pack_bf16(w[2 * c], w[2 * c + 1]) : ptx::pack_f16(w[2 * c], w[2 * c + 1]);
+                packed[16 * cc + c] = pk;
+                if (MODE == M_LUNIF_GRAD) {
+                  st1 += w[2 * c] + w[2 * c + 1];
+                  if (P.fmt) {
+                    st0 += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
+                  } else {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                    st0 += f.x + f.y;
+                  }
+                }
+              }
+            }
+          }
+        }
+        // ---- hand the tile over
+        if (!GRAD) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(BAR_S_EMPTY + b));
+        } else if (P.g_in_tmem) {
+          // weights overwrite the first 32 columns of this warp's own half of the S buffer
+          ptx::tmem_st32(tmem_base + lane_addr + kColS0 + 128u * b + 64u * h, packed);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(BAR_G_FULL));
+        } else {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(BAR_S_EMPTY + b));
+          ptx::mbar_wait(bar(BAR_G_EMPTY), (gt & 1u) ^ 1u, 310);
+          const uint32_t row_addr = sm_g + (uint32_t)h * kSlotBytes + (uint32_t)rrow * 128u;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            ptx::st_shared_v4(row_addr + (uint32_t)((u ^ (rrow & 7)) << 4), packed[4 * u], packed[4 * u + 1],
+                              packed[4 * u + 2], packed[4 * u + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(bar(BAR_G_FULL));
+        }
+      }  // tiles
+
+      // ---- drain the output accumulator of this item
+      if (GRAD && nt > 0) {
+        ptx::mbar_wait(bar(BAR_OUT_FULL), item_cnt & 1u, 320);
+        ptx::tc_fence_after();
+        const int ncol_half = 32 * gch;  // columns of OUT handled by this warp
+        float* orow = P.out + ((int64_t)jp * P.nA + gi) * P.D;
+        for (int c0 = 0; c0 < ncol_half; c0 += 32) {
+          uint32_t v[32];
+          const int ocol = h * ncol_half + c0;
+          ptx::tmem_ld32(tmem_base + lane_addr + kColOut + (uint32_t)ocol, v);
+          ptx::tmem_ld_wait();
+          const int d0 = 256 * split + ocol;
+          if (row_ok) {
+            if (d0 + 32 <= P.D) {
+#pragma unroll
+              for (int c = 0; c < 32; c += 4)
+                *reinterpret_cast<float4*>(orow + d0 + c) = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                                                        __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (d0 + c < P.D) orow[d0 + c] = __uint_as_float(v[c]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(BAR_OUT_EMPTY));
+      }
+      if (row_ok && split == 0) {
+        const int64_t o = ((int64_t)jp * 2 + h) * P.nA + gi;
+        if (MODE == M_LSE) { P.s0[o] = st0; P.s1[o] = st1; }
+        if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
+        if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
+        if (MODE == M_LUNIF_SUM) P.s1[o] = st1;
+        if (MODE == M_SPARSIFY_SUM) P.s0[o] = st0;
+      }
+    }  // items
+  }
+
+  // =========================================================================== teardown
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype) {
+  PFN_encodeTiled enc = get_encode();
+  SCB_CHECK_ARG(enc != nullptr, SCB_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
+  cuuint32_t box[2] = {64u, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(m, dtype == SCB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SCB_CHECK_ARG(r == CUDA_SUCCESS, SCB_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int g_tc_flags = 0;
+
+template <int MODE>
+int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+              TcParams P, cudaStream_t s) {
+  constexpr bool GRAD = (MODE == M_ANCHOR_GRAD || MODE == M_LUNIF_GRAD);
+  SCB_CHECK_ARG(dtype == SCB_BF16 || dtype == SCB_F16, SCB_E_DTYPE, "tensor-core path needs bf16/fp16 operands");
+  SCB_CHECK_ARG(D % 8 == 0 && ldA % 8 == 0 && ldB % 8 == 0, SCB_E_SHAPE, "tensor-core path needs D and ld multiples of 8");
+  SCB_CHECK_ARG(scb_aligned16(A) && scb_aligned16(Bm), SCB_E_ARG, "tensor-core path needs 16-byte aligned operands");
+  if (nA == 0) return 0;
+  SCB_CHECK_ARG(nB > 0, SCB_E_SHAPE, "empty column side");
+  P.nA = nA; P.nB = nB; P.D = D;
+  P.kch = (D + 63) / 64;
+  P.nsplit = (P.kch + 3) / 4;
+  P.n_rb = (int)((nA + 127) / 128);
+  P.n_jb = (int)((nB + 127) / 128);
+  SCB_CHECK_ARG(P.jparts >= 1 && P.jparts <= P.n_jb, SCB_E_ARG, "jparts=%d outside [1, %d]", P.jparts, P.n_jb);
+  P.fmt = (dtype == SCB_BF16) ? 1 : 0;
+  P.g_in_tmem = (GRAD && (g_tc_flags & 1)) ? 1 : 0;
+  P.a_stationary = (P.kch <= 8) ? 1 : 0;
+  const int budget = 232448 - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
+  const int fixed = (P.a_stationary ? P.kch * kSlotBytes : 0) + ((GRAD && !P.g_in_tmem) ? 2 * kSlotBytes : 0);
+  int nstage = (budget - fixed) / kSlotBytes;
+  if (nstage > kMaxStages) nstage = kMaxStages;
+  SCB_CHECK_ARG(nstage >= 4, SCB_E_SHAPE, "not enough shared memory for the tile ring (D=%d)", D);
+  P.nstage = nstage;
+  const size_t smem = (size_t)fixed + (size_t)nstage * kSlotBytes + 3 * 1024;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap(&tmA, A, nA, D, ldA, dtype);
+  if (rc) return rc;
+  rc = make_tmap(&tmB, Bm, nB, D, ldB, dtype);
+  if (rc) return rc;
+
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_pass<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) { scb_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  const int n_items = P.n_rb * (GRAD ? P.nsplit : 1) * P.jparts;
+  const int grid = n_items < num_sms ? n_items : num_sms;
+  k_tc_pass<MODE><<<grid, kThreads, smem, s>>>(tmA, tmB, P);
+  SCB_CHECK_LAUNCH("tc_pass");
+  return 0;
+}
+
+}  // namespace
+
+int scb_tc_set_flags(int flags) { int o = g_tc_flags; g_tc_flags = flags; return o; }
+
+int scb_tc_lse(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype, float scale,
+               int jparts, float* pm, float* pl, cudaStream_t s) {
+  TcParams P{};
+  P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.diag_off = INT64_MIN / 2; P.s0 = pm; P.s1 = pl;
+  return launch_tc<M_LSE>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
+}
+int scb_tc_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                       float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts, float* out,
+                       float* ws, cudaStream_t s) {
+  TcParams P{};
+  P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.rowvec = row_lse; P.colvec = col_lse; P.diag_off = diag_off;
+  P.out = out; P.s0 = ws;
+  return launch_tc<M_ANCHOR_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
+}
+int scb_tc_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll, int dtype,
+                 float t, const float* sqn_r, const float* sqn_all, int64_t row_offset, int jparts, float* U, float* rq,
+                 float* rs, cudaStream_t s) {
+  TcParams P{};
+  P.jparts = jparts; P.p0 = t * SCB_LOG2E; P.rowvec = sqn_r; P.colvec = sqn_all; P.diag_off = row_offset;
+  P.out = U; P.s0 = rq; P.s1 = rs;
+  return U ? launch_tc<M_LUNIF_GRAD>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s)
+           : launch_tc<M_LUNIF_SUM>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
+}
+int scb_tc_sparsify_sum(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
+                        int dtype, int64_t row_offset, int jparts, float* rs, cudaStream_t s) {
+  TcParams P{};
+  P.jparts = jparts; P.diag_off = row_offset; P.s0 = rs;
+  return launch_tc<M_SPARSIFY_SUM>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
+}

@@ -1,0 +1,307 @@
+"""Drop-in replacements for the loss functions of noostale/sparsify-clip.
+
+Same names, positional order and defaults as the reference (sparsify_clip.py:110-187,
+:308-355, :487-505), so a copy of its training loop runs unchanged with
+``from sparsify_clip_b200 import *``.  Each function is a ``torch.autograd.Function`` over
+the C-ABI CUDA library (include/scb200.h): the B x B similarity / distance matrices are
+produced tile by tile on the tensor cores and never reach memory.
+
+Every function takes an optional keyword ``group`` (a ``torch.distributed`` process group,
+or ``True`` for the default group).  With a group, the inputs are this rank's ROW SHARD of
+the global batch (equal shard sizes); the returned loss is the full-batch loss (identical on
+all ranks) and the gradient is this rank's slice of the full-batch gradient.  Exchange steps:
+all-gather of the [B, D] operands and of the 2 B LSE values, all-reduce of scalar partials.
+No gradient reduce-scatter is needed: each rank recomputes its own row block of S for dI and
+its own column block for dT.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from .backend_cuda import get_backend
+
+__all__ = [
+    "contrastive_loss", "lunif_loss", "lalign_loss", "compute_centroids_only", "compute_centroids",
+    "sparsify_loss", "random_alignment_loss", "contrastive_loss_roberta", "centroid_alignment_loss",
+    "normalized_centroids", "l2_normalize",
+]
+
+
+# ----------------------------------------------------------------------------- distributed helpers
+def _resolve_group(group):
+    if group is None or group is False:
+        return None
+    if group is True:
+        return dist.group.WORLD
+    return group
+
+
+def _world(group):
+    return (dist.get_rank(group), dist.get_world_size(group)) if group is not None else (0, 1)
+
+
+def _all_gather_rows(x, group):
+    if group is None:
+        return x
+    ws = dist.get_world_size(group)
+    x = x.contiguous()
+    out = torch.empty((ws * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x, group=group)
+    return out
+
+
+def _all_reduce_(x, group):
+    if group is not None:
+        dist.all_reduce(x, group=group)
+    return x
+
+
+def _common(a, b):
+    """Bring two operands to one dtype (the wider of the two)."""
+    if a.dtype != b.dtype:
+        dt = torch.promote_types(a.dtype, b.dtype)
+        a, b = a.to(dt), b.to(dt)
+    return a, b
+
+
+def _gout32(g):
+    return g.detach().to(torch.float32).reshape(()).contiguous()
+
+
+# ----------------------------------------------------------------------------- anchor (CLIP InfoNCE)
+class _AnchorFn(torch.autograd.Function):
+    """sparsify_clip.py:110-132.  forward: two LSE sweeps (rows of S, rows of S^T) + diagonal;
+    backward: one recompute sweep per operand (flash-style), d/dtau from the same sweep."""
+
+    @staticmethod
+    def forward(ctx, I, T, tau_t, tau_f, group):
+        be = get_backend()
+        I, T = _common(I, T)
+        Ip, Tp = be.prep(I), be.prep(T)
+        tau = float(tau_t) if tau_t is not None else float(tau_f)
+        scale = 1.0 / tau
+        rank, ws = _world(group)
+        n = Ip.shape[0]
+        I_all, T_all = _all_gather_rows(Ip, group), _all_gather_rows(Tp, group)
+        r = be.lse(Ip, T_all, scale)                  # row LSE of the local rows of S
+        c = be.lse(Tp, I_all, scale)                  # column LSE of the local columns of S
+        diag = be.row_dot(Ip, Tp)
+        part = be.sum(r) + be.sum(c) - (2.0 * scale) * be.sum(diag)
+        _all_reduce_(part, group)
+        B = n * ws
+        ctx.group, ctx.scale, ctx.B, ctx.off = group, scale, B, rank * n
+        ctx.in_dtypes = (I.dtype, T.dtype)
+        ctx.tau_meta = None if tau_t is None else (tau_t.dtype, tau_t.device, tau_t.shape)
+        ctx.save_for_backward(Ip, Tp, I_all, T_all, r, c, diag)
+        return part / (2.0 * B)
+
+    @staticmethod
+    def backward(ctx, gout):
+        be = get_backend()
+        Ip, Tp, I_all, T_all, r, c, diag = ctx.saved_tensors
+        group, scale, B, off = ctx.group, ctx.scale, ctx.B, ctx.off
+        g = _gout32(gout)
+        need_I, need_T, need_tau = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        r_all, c_all = _all_gather_rows(r, group), _all_gather_rows(c, group)
+        coef = scale / (2.0 * B)
+        dI = dT = dtau = None
+        ws_sum = None
+        if need_I or need_tau:
+            dI, ws_sum = be.anchor_grad(Ip, T_all, Tp, scale, r, c_all, c, diag, off, coef, g, need_tau)
+            dI = dI.to(ctx.in_dtypes[0]) if need_I else None
+        if need_T:
+            dT, _ = be.anchor_grad(Tp, I_all, Ip, scale, c, r_all, r, diag, off, coef, g, False)
+            dT = dT.to(ctx.in_dtypes[1])
+        if need_tau:
+            # d/dtau = -(1/tau) sum_ij G_ij S_ij,  G = (P + Q - 2 I_B)/(2B),  S = scale * (a.b)
+            part = ws_sum - 2.0 * be.sum(diag)
+            _all_reduce_(part, group)
+            dt, dev, shp = ctx.tau_meta
+            dtau = (part * g * (-(scale * scale) / (2.0 * B))).to(device=dev, dtype=dt).reshape(shp)
+        return dI, dT, dtau, None, None
+
+
+def contrastive_loss(image_embeds, text_embeds, temperature=0.07, *, group=None):
+    """CLIP anchor loss; `temperature` divides the logits (sparsify_clip.py:119-120) and may be a
+    float or a 0-dim tensor / nn.Parameter on CPU or CUDA (its gradient comes back on its device)."""
+    group = _resolve_group(group)
+    if isinstance(temperature, torch.Tensor):
+        return _AnchorFn.apply(image_embeds, text_embeds, temperature, None, group)
+    return _AnchorFn.apply(image_embeds, text_embeds, None, float(temperature), group)
+
+
+# ----------------------------------------------------------------------------- L_unif
+class _LunifFn(torch.autograd.Function):
+    """sparsify_clip.py:159-164.  When a gradient is needed the forward is a SINGLE sweep that
+    yields the loss and the unscaled gradient together (W.X on the tensor cores right behind the
+    Gram tile); backward is one element-wise multiply by grad_output."""
+
+    @staticmethod
+    def forward(ctx, x, t, group):
+        be = get_backend()
+        xp = be.prep(x)
+        rank, ws = _world(group)
+        n = xp.shape[0]
+        x_all = _all_gather_rows(xp, group)
+        need = ctx.needs_input_grad[0]
+        core = be.lunif_core(xp, x_all, float(t), rank * n, need)
+        rs = _all_reduce_(core["rs_sum"], group)
+        B = n * ws
+        ssum = rs * 0.5
+        loss = torch.log(ssum / (B * (B - 1) / 2.0))          # B == 1 -> log(0/0) = nan, as the reference
+        if need:
+            inv = (-2.0 * float(t)) / ssum
+            gx = be.lunif_grad(core, xp, 1.0, inv.contiguous())
+            ctx.save_for_backward(gx)
+            ctx.in_dtype = x.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        (gx,) = ctx.saved_tensors
+        return (gx * _gout32(gout)).to(ctx.in_dtype), None, None
+
+
+def lunif_loss(x, t=2, *, group=None):
+    return _LunifFn.apply(x, t, _resolve_group(group))
+
+
+# ----------------------------------------------------------------------------- L_align
+class _LalignFn(torch.autograd.Function):
+    """sparsify_clip.py:186-187 with alpha = 2."""
+
+    @staticmethod
+    def forward(ctx, x, y, group):
+        be = get_backend()
+        x, y = _common(x, y)
+        xp, yp = be.prep(x), be.prep(y)
+        _, ws = _world(group)
+        part = _all_reduce_(be.sum(be.lalign_rows(xp, yp)), group)
+        ctx.B = xp.shape[0] * ws
+        ctx.in_dtypes = (x.dtype, y.dtype)
+        ctx.save_for_backward(xp, yp)
+        return part / ctx.B
+
+    @staticmethod
+    def backward(ctx, gout):
+        be = get_backend()
+        xp, yp = ctx.saved_tensors
+        dX, dY = be.lalign_bwd(xp, yp, 2.0 / ctx.B, _gout32(gout), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return (None if dX is None else dX.to(ctx.in_dtypes[0]),
+                None if dY is None else dY.to(ctx.in_dtypes[1]), None)
+
+
+def lalign_loss(x, y, alpha=2, *, group=None):
+    if alpha != 2:
+        # the reference only ever calls alpha=2 (all YAMLs); other exponents stay in PyTorch
+        return (x - y).norm(dim=1).pow(alpha).mean()
+    return _LalignFn.apply(x, y, _resolve_group(group))
+
+
+# ----------------------------------------------------------------------------- centroids / normalise
+class _CentroidFn(torch.autograd.Function):
+    """normalize((a + b)/2, eps=1e-12): sparsify_clip.py:353 + F.normalize at :804, fused."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        be = get_backend()
+        a, b = _common(a, b)
+        ap, bp = be.prep(a), be.prep(b)
+        C, inv = be.centroid_fwd(ap, bp, ap.dtype)
+        ctx.in_dtypes = (a.dtype, b.dtype)
+        ctx.save_for_backward(ap, bp, inv)
+        return C
+
+    @staticmethod
+    def backward(ctx, dC):
+        be = get_backend()
+        ap, bp, inv = ctx.saved_tensors
+        dA, dB = be.centroid_bwd(ap, bp, dC.detach().to(torch.float32).contiguous(), inv)
+        return dA.to(ctx.in_dtypes[0]), dB.to(ctx.in_dtypes[1])
+
+
+def normalized_centroids(a, b):
+    """F.normalize(compute_centroids_only(a, b), dim=-1) in one kernel (forward and backward)."""
+    return _CentroidFn.apply(a, b)
+
+
+class _NormalizeFn(torch.autograd.Function):
+    """e / e.norm(dim=-1, keepdim=True)  (no eps) -- sparsify_clip.py:772-773."""
+
+    @staticmethod
+    def forward(ctx, x):
+        be = get_backend()
+        xp = be.prep(x)
+        Y, inv = be.normalize_fwd(xp, xp.dtype)
+        ctx.in_dtype = x.dtype
+        ctx.save_for_backward(xp, inv)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        be = get_backend()
+        xp, inv = ctx.saved_tensors
+        return be.normalize_bwd(xp, dY.detach().to(torch.float32).contiguous(), inv).to(ctx.in_dtype)
+
+
+def l2_normalize(x):
+    return _NormalizeFn.apply(x)
+
+
+def compute_centroids_only(text_embeddings, visual_embeddings):
+    """(a + b) / 2 -- sparsify_clip.py:334-355 (the call sites pass (image, text); symmetric)."""
+    return (text_embeddings + visual_embeddings) / 2.0
+
+
+def compute_centroids(text_embeddings, visual_embeddings):
+    """All-pairs centroids [B1, B2, D] and their norms -- sparsify_clip.py:308-332 (never called by
+    the reference; kept for the signature surface, O(B1*B2*D) memory by definition)."""
+    centroids = (text_embeddings.unsqueeze(1) + visual_embeddings.unsqueeze(0)) / 2.0
+    return torch.norm(centroids, dim=-1), centroids
+
+
+# ----------------------------------------------------------------------------- cold variants
+class _SparsifyFn(torch.autograd.Function):
+    """mse(x x^T, 2 eye - 1) -- sparsify_clip.py:166-176.  Forward on the Gram-tile kernel;
+    backward (4/B^2)(E X) stays in PyTorch (cold path: no YAML selects this loss)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        be = get_backend()
+        xp = be.prep(x)
+        B = xp.shape[0]
+        ctx.save_for_backward(x)
+        return be.sparsify_sum(xp, xp, 0) / float(B * B)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (x,) = ctx.saved_tensors
+        xf = x.detach().float()
+        B = xf.shape[0]
+        E = xf @ xf.t() - (2.0 * torch.eye(B, device=xf.device) - 1.0)
+        return ((4.0 / (B * B)) * (E @ xf) * _gout32(gout)).to(x.dtype)
+
+
+def sparsify_loss(x):
+    return _SparsifyFn.apply(x)
+
+
+def random_alignment_loss(x, y):
+    """sparsify_clip.py:178-184: L_align against a random permutation of y."""
+    idx = torch.randperm(y.size(0), device=y.device)
+    return lalign_loss(x, y[idx])
+
+
+def contrastive_loss_roberta(image_embeds, text_embeds, roberta_similarity, temperature=0.07):
+    """Soft-target variant, sparsify_clip.py:135-157.  Dead code in the reference (only referenced
+    from a string literal); it needs a dense B x B target matrix as INPUT, so it stays in PyTorch."""
+    logits = image_embeds @ text_embeds.t() / temperature
+    li = torch.nn.functional.cross_entropy(logits, roberta_similarity)
+    lt = torch.nn.functional.cross_entropy(logits.t(), roberta_similarity.t())
+    return (li + lt) / 2
+
+
+def centroid_alignment_loss(img_embeds, txt_embeds, p=2):
+    """|| mean(img) - mean(txt) ||_p -- sparsify_clip.py:487-505 (O(B*D), unused by the YAMLs)."""
+    return torch.norm(img_embeds.mean(dim=0) - txt_embeds.mean(dim=0), p=p)
