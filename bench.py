@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- loss fwd+bwd pairs/s of the sparsify-clip contrastive-loss hot path on B200.
+
+Workload (BASELINE.json metric, config c3): experiment_3 composition
+    loss = anchor(I, T, tau=0.1) + lalign(I, T) + (lunif(I) + lunif(T)) / 2
+forward + backward (gradients w.r.t. I and T materialised), global B = 32768, D = 512, bf16
+unit-norm synthetic embeddings.  At N > 1 the rows are sharded over the ranks ("strong" scaling:
+the global batch is fixed, as BASELINE.json quotes it), one process per GPU under torchrun.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  `value` = global B / device time per step with inputs resident in
+HBM; `e2e` = the same step through the public API from pinned HOST buffers (H2D copy of I and T and
+D2H read of the loss inside the timed region); `roofline` = algorithmic FLOPs of the B x B passes /
+their summed CUDA-event duration against the measured bf16 peak; `cpu_baseline` = the torch port of
+the reference op sequence (oracle/torch_port.py) on the host cores, on a bounded sample.
+`--impl reference` times that CPU path alone and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "loss_fwd_bwd_pairs_per_s"
+UNIT = "pairs/s"
+WEIGHTS_EXP3 = dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0, alpha=0.0, beta=0.0)
+TAU = 0.1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32768, help="global batch B")
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--cpu-sample-batch", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc-flags", type=int, default=None, help="debug: scb_set_tc_flags value")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_time(batch, dim, steps, warmup):
+    """torch port of the reference op sequence, fp32, all host threads; returns (median s/step, threads)."""
+    import torch
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(42)
+    I = torch.nn.functional.normalize(torch.randn(batch, dim, generator=g), dim=-1)
+    T = torch.nn.functional.normalize(I + 0.5 * torch.randn(batch, dim, generator=g), dim=-1)
+    w = (1.0, 1.0, 0.5, 0.5, 0.0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        torch_port.fwd_bwd(I, T, TAU, w)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return statistics.median(times), torch.get_num_threads()
+
+
+def cpu_baseline_record(args, steps=3, warmup=1):
+    bs = min(args.cpu_sample_batch, args.batch)
+    t, threads = cpu_reference_step_time(bs, args.dim, steps, warmup)
+    t_full = t * (args.batch / bs) ** 2          # every term but L_align is O(B^2 D)
+    return {"value": args.batch / t_full, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"oracle/torch_port.py exp-3 fwd+bwd fp32 at B={bs}, D={args.dim}: median {t:.3f} s/step over "
+                      f"{steps} steps = {bs / t:.1f} pairs/s measured; value extrapolated to B={args.batch} by (B/{bs})^2"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    bs = min(args.cpu_sample_batch, args.batch)
+    t, threads = cpu_reference_step_time(bs, args.dim, steps, warmup)
+    t_full = t * (args.batch / bs) ** 2
+    value = args.batch / t_full
+    sample = (f"each step = oracle/torch_port.py exp-3 fwd+bwd fp32 on a B={bs} sample (median {t:.3f} s); "
+              f"value and ms_per_step extrapolated to B={args.batch} by (B/{bs})^2")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"c3: experiment_3 anchor+lalign+(lunif(img)+lunif(txt))/2, B={args.batch}, D={args.dim}, "
+                                   f"tau={TAU}, CPU torch port of the reference ops"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sparsify_clip_b200 as scb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    be = scb.get_backend()
+    if args.tc_flags is not None:
+        be.lib.scb_set_tc_flags(args.tc_flags)
+
+    B, D = args.batch, args.dim
+    assert B % world == 0, "global batch must divide over the ranks"
+    n = B // world
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    I0 = torch.nn.functional.normalize(torch.randn(n, D, generator=g, device=dev), dim=-1)
+    T0 = torch.nn.functional.normalize(I0 + 0.5 * torch.randn(n, D, generator=g, device=dev), dim=-1)
+    I = I0.to(torch.bfloat16).requires_grad_(True)
+    T = T0.to(torch.bfloat16).requires_grad_(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(Iv, Tv):
+        Iv.grad = None
+        Tv.grad = None
+        loss = scb.weighted_loss(Iv, Tv, TAU, WEIGHTS_EXP3, group=group)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(I, T)
+    barrier()
+
+    # ---- timed region: K steps, each bracketed by CUDA events, L2 flushed (untimed) in between
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    launches0 = be.launches
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        loss = step(I, T)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = be.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = tt.item() / args.steps
+    value = B / (ms_per_step * 1e-3)
+    loss_val = float(loss.item())
+
+    # ---- per-pass CUDA-event timing (separate instrumented steps) for the roofline line
+    be.pass_events = []
+    prof_steps = 3
+    for _ in range(prof_steps):
+        flush.zero_()
+        step(I, T)
+    torch.cuda.synchronize()
+    per = {}
+    for name, a, b in be.pass_events:
+        per.setdefault(name, []).append(a.elapsed_time(b))
+    be.pass_events = None
+    pass_ms = sum(sum(v) for v in per.values()) / prof_steps
+    pm = torch.tensor([pass_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+    pass_ms = pm.item()
+    flops_alg = 14.0 * B * B * D                       # anchor 6 + 2 x lunif 4 (B^2 D each)
+    peak, peak_src = peaks()
+    achieved = flops_alg / world / (pass_ms * 1e-3) / 1e12      # per-GPU TFLOP/s of the B x B passes
+
+    # ---- end to end through the public API from pinned host memory
+    hI = I0.to(torch.bfloat16).cpu().pin_memory()
+    hT = T0.to(torch.bfloat16).cpu().pin_memory()
+    dI = torch.empty(n, D, dtype=torch.bfloat16, device=dev)
+    dT = torch.empty(n, D, dtype=torch.bfloat16, device=dev)
+    hloss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        dI.copy_(hI, non_blocking=True)
+        dT.copy_(hT, non_blocking=True)
+        Iv = dI.detach().requires_grad_(True)
+        Tv = dT.detach().requires_grad_(True)
+        l = step(Iv, Tv)
+        hloss.copy_(l.detach(), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_ev = []
+    ke = max(3, min(args.steps, 10))
+    for _ in range(ke):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_step()
+        e1.record()
+        e2e_ev.append((e0, e1))
+    barrier()
+    et = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev) / ke], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+    e2e_value = B / (et.item() * 1e-3)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"c3: experiment_3 anchor+lalign+(lunif(img)+lunif(txt))/2 fwd+bwd, global B={B}, D={D}, "
+                                   f"tau={TAU}, bf16 unit-norm rows, rows sharded over {world} GPU(s)",
+                       "l2": "256 MiB buffer written between timed iterations (untimed); per-step scratch also exceeds the 126 MB L2",
+                       "timing": "sum of per-step CUDA-event intervals, max over ranks"},
+            "loss": loss_val,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * D * 2, "d2h_bytes_per_step": 4,
+                    "ms_per_step": et.item()},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "k_tc_pass<MODE> (2 LSE + 2 anchor-grad + 2 lunif launches per step)",
+                         "algorithmic_flops_per_step": flops_alg, "passes_ms_per_step": pass_ms,
+                         "per_pass_ms": {k: sum(v) / prof_steps for k, v in per.items()},
+                         "whole_step_frac": flops_alg / world / (ms_per_step * 1e-3) / 1e12 / peak},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline_record(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

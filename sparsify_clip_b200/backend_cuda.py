@@ -55,6 +55,30 @@ class CudaBackend:
 
     def __init__(self):
         self.lib = _lib.load()
+        self.launches = 0          # kernels launched through this backend (bench.py reports it)
+        self.pass_events = None    # when a list: (name, start_event, end_event) per B x B pass
+
+    def _count(self, n=1):
+        self.launches += n
+
+    class _Timed:
+        """Optional CUDA-event bracket around one B x B pass (enabled by bench.py only)."""
+
+        def __init__(self, be, name):
+            self.be, self.name = be, name
+
+        def __enter__(self):
+            if self.be.pass_events is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e1 = torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+            return self
+
+        def __exit__(self, *exc):
+            if self.be.pass_events is not None:
+                self.e1.record()
+                self.be.pass_events.append((self.name, self.e0, self.e1))
+            return False
 
     # ------------------------------------------------------------------ tensor plumbing
     def prep(self, x):
@@ -99,6 +123,7 @@ class CudaBackend:
         scratch = torch.empty(1024, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             check(self.lib.scb_sum(_ptr(x), x.numel(), _ptr(scratch), _ptr(out), self._stream()), "sum")
+        self._count(2)
         return out
 
     # ------------------------------------------------------------------ row-wise
@@ -107,6 +132,7 @@ class CudaBackend:
         with torch.cuda.device(x.device):
             check(self.lib.scb_row_sqnorm(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _DT[x.dtype], _ptr(out),
                                           self._stream()), "row_sqnorm")
+        self._count()
         return out
 
     def row_dot(self, a, b):
@@ -114,6 +140,7 @@ class CudaBackend:
         with torch.cuda.device(a.device):
             check(self.lib.scb_row_dot(_ptr(a), _ptr(b), a.shape[0], a.shape[1], a.stride(0), b.stride(0), _DT[a.dtype],
                                        _ptr(out), self._stream()), "row_dot")
+        self._count()
         return out
 
     def lalign_rows(self, x, y):
@@ -121,6 +148,7 @@ class CudaBackend:
         with torch.cuda.device(x.device):
             check(self.lib.scb_lalign_rows(_ptr(x), _ptr(y), x.shape[0], x.shape[1], x.stride(0), y.stride(0),
                                            _DT[x.dtype], _ptr(out), self._stream()), "lalign_rows")
+        self._count()
         return out
 
     def lalign_bwd(self, x, y, host_scale, dev_scale, want_x=True, want_y=True):
@@ -130,6 +158,7 @@ class CudaBackend:
         with torch.cuda.device(x.device):
             check(self.lib.scb_lalign_bwd(_ptr(x), _ptr(y), n, D, x.stride(0), y.stride(0), _DT[x.dtype], host_scale,
                                           _ptr(dev_scale), 0, _ptr(dX), _ptr(dY), self._stream()), "lalign_bwd")
+        self._count()
         return dX, dY
 
     def centroid_fwd(self, a, b, out_dtype):
@@ -139,6 +168,7 @@ class CudaBackend:
         with torch.cuda.device(a.device):
             check(self.lib.scb_centroid_fwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(C),
                                             _DT[out_dtype], _ptr(inv), self._stream()), "centroid_fwd")
+        self._count()
         return C, inv
 
     def centroid_bwd(self, a, b, dC, inv, host_scale=1.0, dev_scale=None):
@@ -149,6 +179,7 @@ class CudaBackend:
             check(self.lib.scb_centroid_bwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(dC),
                                             _ptr(inv), host_scale, _ptr(dev_scale), 0, _ptr(dA), _ptr(dB),
                                             self._stream()), "centroid_bwd")
+        self._count()
         return dA, dB
 
     def normalize_fwd(self, x, out_dtype):
@@ -158,6 +189,7 @@ class CudaBackend:
         with torch.cuda.device(x.device):
             check(self.lib.scb_normalize_fwd(_ptr(x), n, D, x.stride(0), _DT[x.dtype], _ptr(Y), _DT[out_dtype],
                                              _ptr(inv), self._stream()), "normalize_fwd")
+        self._count()
         return Y, inv
 
     def normalize_bwd(self, x, dY, inv):
@@ -166,6 +198,7 @@ class CudaBackend:
         with torch.cuda.device(x.device):
             check(self.lib.scb_normalize_bwd(_ptr(x), n, D, x.stride(0), _DT[x.dtype], _ptr(dY), _ptr(inv), _ptr(dX),
                                              self._stream()), "normalize_bwd")
+        self._count()
         return dX
 
     # ------------------------------------------------------------------ B x B passes
@@ -180,8 +213,10 @@ class CudaBackend:
         pl = torch.empty_like(pm)
         out = torch.empty(nA, dtype=torch.float32, device=A.device)
         with torch.cuda.device(A.device):
-            check(self.lib.scb_lse_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0), _DT[A.dtype],
-                                        float(scale), jp, _ptr(pm), _ptr(pl), path, self._stream()), "lse_pass")
+            with self._Timed(self, "lse"):
+                check(self.lib.scb_lse_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0), _DT[A.dtype],
+                                            float(scale), jp, _ptr(pm), _ptr(pl), path, self._stream()), "lse_pass")
+            self._count(2)
             check(self.lib.scb_lse_combine(_ptr(pm), _ptr(pl), jp * nsub, nA, _ptr(out), self._stream()), "lse_combine")
         return out
 
@@ -198,9 +233,12 @@ class CudaBackend:
         ws = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
         dA = torch.empty(nA, D, dtype=torch.float32, device=A.device)
         with torch.cuda.device(A.device):
-            check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0), _DT[A.dtype],
-                                                float(scale), _ptr(row_lse), _ptr(col_lse_all), int(diag_off), jp,
-                                                _ptr(out), _ptr(ws), path, self._stream()), "anchor_grad_pass")
+            with self._Timed(self, "anchor_grad"):
+                check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0),
+                                                    _DT[A.dtype], float(scale), _ptr(row_lse), _ptr(col_lse_all),
+                                                    int(diag_off), jp, _ptr(out), _ptr(ws), path, self._stream()),
+                      "anchor_grad_pass")
+            self._count(2)
             check(self.lib.scb_anchor_grad_finalize(_ptr(out), jp, nA, D, _ptr(V_rows), V_rows.stride(0), _DT[V_rows.dtype],
                                                     _ptr(row_lse), _ptr(col_lse_rows), _ptr(diag), float(scale),
                                                     float(host_scale), _ptr(dev_scale), 0, _ptr(dA), self._stream()),
@@ -225,14 +263,17 @@ class CudaBackend:
             if need_grad:
                 U = torch.empty(jp, nR, D, dtype=torch.float32, device=Xr.device)
                 rq = torch.empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
-                check(self.lib.scb_lunif_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0), _DT[Xr.dtype],
-                                              float(t), _ptr(sqn_r), _ptr(sqn_all), int(row_offset), jp, _ptr(U), _ptr(rq),
-                                              _ptr(rs), path, self._stream()), "lunif_pass")
+                with self._Timed(self, "lunif"):
+                    check(self.lib.scb_lunif_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),
+                                                  _DT[Xr.dtype], float(t), _ptr(sqn_r), _ptr(sqn_all), int(row_offset), jp,
+                                                  _ptr(U), _ptr(rq), _ptr(rs), path, self._stream()), "lunif_pass")
+                self._count()
                 core.update(U=U, rq=rq)
             else:
                 check(self.lib.scb_lunif_sum_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),
                                                   _DT[Xr.dtype], float(t), _ptr(sqn_r), _ptr(sqn_all), int(row_offset), jp,
                                                   _ptr(rs), path, self._stream()), "lunif_sum_pass")
+                self._count()
         core["rs_sum"] = self.sum(rs)
         return core
 
@@ -244,6 +285,7 @@ class CudaBackend:
             check(self.lib.scb_lunif_grad_finalize(_ptr(core["U"]), core["jparts"], _ptr(core["rq"]), core["nparts"], nR, D,
                                                    _ptr(Xr), Xr.stride(0), _DT[Xr.dtype], float(host_scale), _ptr(dev_scale),
                                                    0, _ptr(dX), self._stream()), "lunif_grad_finalize")
+        self._count()
         return dX
 
     def sparsify_sum(self, Xr, Xall, row_offset):
@@ -257,6 +299,7 @@ class CudaBackend:
             check(self.lib.scb_sparsify_sum_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),
                                                  _DT[Xr.dtype], int(row_offset), jp, _ptr(rs), path, self._stream()),
                   "sparsify_sum_pass")
+        self._count()
         return self.sum(rs)
 
 

@@ -1,0 +1,79 @@
+"""TEST DOUBLE for sparsify_clip_b200.backend_cuda.CudaBackend: the same interface implemented with
+dense torch fp64 CPU math (oracle formulas).  Lets the CPU suite exercise the host logic of
+losses.py -- sharding offsets, all-gathers, scalar assembly, autograd wiring -- under gloo.
+Never imported by the product."""
+import torch
+
+
+class FakeBackend:
+    name = "fake-cpu"
+    launches = 0
+    pass_events = None
+
+    def prep(self, x):
+        return x.detach().double().contiguous()
+
+    def sum(self, x):
+        return x.double().sum()
+
+    def row_sqnorm(self, x):
+        return (x * x).sum(1)
+
+    def row_dot(self, a, b):
+        return (a * b).sum(1)
+
+    def lalign_rows(self, x, y):
+        return ((x - y) ** 2).sum(1)
+
+    def lalign_bwd(self, x, y, host_scale, dev_scale, want_x=True, want_y=True):
+        g = host_scale * dev_scale.double() * (x - y)
+        return (g if want_x else None), (-g if want_y else None)
+
+    def centroid_fwd(self, a, b, out_dtype):
+        m = (a + b) / 2
+        inv = 1.0 / m.norm(dim=1).clamp_min(1e-12)
+        return m * inv[:, None], inv
+
+    def centroid_bwd(self, a, b, dC, inv, host_scale=1.0, dev_scale=None):
+        c = (a + b) / 2 * inv[:, None]
+        dC = dC.double()
+        dm = (dC - c * (c * dC).sum(1, keepdim=True)) * inv[:, None] * 0.5 * host_scale
+        return dm, dm.clone()
+
+    def lse(self, A, Ball, scale):
+        return torch.logsumexp(scale * A @ Ball.t(), dim=1)
+
+    def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off, host_scale,
+                    dev_scale, want_ws):
+        G0 = A @ Ball.t()
+        S = scale * G0
+        W = torch.exp(S - row_lse[:, None]) + torch.exp(S - col_lse_all[None, :])
+        ws = (W * G0).sum() if want_ws else None
+        idx = torch.arange(A.shape[0])
+        Wd = W.clone()
+        Wd[idx, idx + diag_off] = 0
+        sii = scale * diag
+        dcoef = torch.exp(sii - row_lse) + torch.exp(sii - col_lse_rows) - 2
+        dA = host_scale * dev_scale.double() * (Wd @ Ball + dcoef[:, None] * V_rows)
+        return dA, ws
+
+    def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None):
+        n = (Xall * Xall).sum(1)
+        nr = (Xr * Xr).sum(1)
+        d2 = (nr[:, None] + n[None, :] - 2 * Xr @ Xall.t()).clamp_min(0)
+        W = torch.exp(-t * d2)
+        idx = torch.arange(Xr.shape[0])
+        W[idx, idx + row_offset] = 0
+        core = {"rs_sum": W.sum()}
+        if need_grad:
+            core.update(U=W @ Xall, rq=W.sum(1))
+        return core
+
+    def lunif_grad(self, core, Xr, host_scale, dev_scale):
+        return host_scale * dev_scale.double() * (core["rq"][:, None] * Xr - core["U"])
+
+    def sparsify_sum(self, Xr, Xall, row_offset):
+        E = Xr @ Xall.t() + 1.0
+        idx = torch.arange(Xr.shape[0])
+        E[idx, idx + row_offset] -= 2.0
+        return (E * E).sum()

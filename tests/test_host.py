@@ -1,0 +1,172 @@
+"""CPU suite: C-ABI surface, host logic (ladder, schedules, work split), loud failure without CUDA,
+and the sharded (world_size 2, gloo) algebra of losses.py against the oracle."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import sparsify_clip_b200 as scb
+from oracle import closed_form as cf
+from sparsify_clip_b200 import _lib, backend_cuda
+from tests._fake_backend import FakeBackend
+
+YAML_LOSS_TYPES = [  # loss_type strings of the 10 experiment + 3 ablation YAMLs (experiments_configs/*.yaml:19)
+    ("anchor", 0), ("anchor", 0),
+    ("only_lunif_n_then_anchor+lalign+lunif(text)+lunif(img)", 0),
+    ("only_lunif_n_then_anchor+lalign+lunif(centroids)", 0),
+    ("only_lunif_n_then_anchor+lalign+lunif(text)+lunif(img)", 1),
+    ("only_lunif_n_then_anchor+lalign+lunif(centroids)", 1),
+    ("only_lunif_n_then_anchor+lalign+BETA*lunif(centroids)", 0),
+    ("only_lunif_n_then_anchor+lalign+BETA*lunif(centroids)", 0),
+    ("only_lunif_n_then_anchor+ALPHA*lalign+BETA*(lunif(text)+lunif(img))", 0),
+    ("only_lunif_n_then_anchor+ALPHA*lalign+BETA*lunif(centroids)", 0),
+    ("ANCHOR(IMAGE,TEXT)+LALIGN(IMAGE,TEXT)+LUNIF(CENTROIDS)", 0),
+    ("ANCHOR(IMAGE,TEXT)+LALIGN(IMAGE,TEXT)", 0),
+    ("ANCHOR(IMAGE,TEXT)+LUNIF(CENTROIDS)", 0),
+]
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _lib.header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/scb200.h but not exported"
+    assert set(_lib.SIGNATURES) | {"scb_last_error"} == set(declared)
+    assert _lib.load().scb_version() >= 100
+    assert _lib.load().scb_pass_nsub(_lib.PATH_TC) == 2 and _lib.load().scb_pass_nsub(_lib.PATH_SIMT) == 1
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    lib = _lib.load()
+    rc = lib.scb_row_sqnorm(None, 4, 8, 8, 7, None, None)       # bad dtype
+    assert rc == -2 and b"dtype" in lib.scb_last_error()
+    rc = lib.scb_lse_pass(None, 4, None, 4, 8, 8, 8, _lib.SCB_BF16, 1.0, 0, None, None, _lib.PATH_TC, None)
+    assert rc == -1
+    with pytest.raises(ValueError):
+        _lib.check(rc, "lse_pass")
+
+
+def test_no_cpu_fallback():
+    x = torch.randn(8, 16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        scb.lunif_loss(x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        scb.contrastive_loss(x, x, 0.1)
+
+
+@pytest.mark.parametrize("lt,warm", YAML_LOSS_TYPES)
+def test_ladder_matches_oracle(lt, warm):
+    cfg = {"loss_type": lt, "only_lunif_epochs": warm, "beta_warmup_epoch": 20, "beta_decay_epoch": 50,
+           "alpha_warmup_epoch": 50, "alpha_increment_epoch": 50}
+    for epoch in (0, 1, 30):
+        for step in (1, 150, 330, 777, 5000):
+            w = scb.ladder_weights(cfg, epoch, step, 1000)
+            ref = cf.ladder_terms(cfg, epoch, step, 1000)
+            got = (w["anchor"], w["align"], w["unif_img"], w["unif_txt"], w["unif_cen"])
+            assert got == pytest.approx(ref, abs=0), (lt, epoch, step)
+
+
+def test_ladder_quirks():
+    cfg = {"loss_type": "only_lunif_n_then_anchor+lalign+BETA*lunif(centroids)", "only_lunif_epochs": 0,
+           "beta_warmup_epoch": 20, "beta_decay_epoch": 50}
+    w = scb.ladder_weights(cfg, 0, 450, 1000)          # exp 7 AND exp 8 run the modality variant (:813 wins)
+    assert w["unif_cen"] == 0.0 and w["unif_img"] == pytest.approx(0.25)
+    cfg["loss_type"] += "[intended]"
+    assert scb.ladder_weights(cfg, 0, 450, 1000)["unif_cen"] == pytest.approx(0.5)
+    with pytest.raises(KeyError):
+        scb.ladder_weights({"loss_type": "nope", "only_lunif_epochs": 0}, 0, 1, 10)
+    for s in (0, 199, 200, 450, 700, 10 ** 6):
+        assert scb.get_beta(s, 1000, 20, 50) == cf.get_beta(s, 1000, 20, 50)
+        assert scb.get_alpha(s, 1000, 50, 50) == cf.get_alpha(s, 1000, 50, 50)
+    assert scb.get_beta(5, 10) == cf.get_beta(5, 10) and scb.get_alpha(5, 10) == cf.get_alpha(5, 10)
+
+
+def test_reference_yaml_strings_if_present():
+    import glob
+    files = glob.glob("/root/reference/experiments_configs/*.yaml") + glob.glob("/root/reference/ablatation_configs/*.yaml")
+    if not files:
+        pytest.skip("reference not present")
+    import yaml
+    seen = 0
+    for f in files:
+        cfg = yaml.safe_load(open(f))
+        if not cfg:
+            continue
+        assert cfg["loss_type"] in scb.LOSS_TYPES, f
+        seen += 1
+    assert seen == 13
+
+
+def test_choose_jparts():
+    assert scb.choose_jparts(256, 2, 256, 148) == 2          # c3 gradient sweeps: 1024 items -> 7 rounds
+    assert scb.choose_jparts(1, 1, 1, 148) == 1
+    for n_rb, ns, n_jb in [(32, 2, 32), (8, 2, 8), (256, 1, 256), (512, 3, 512), (3, 1, 100)]:
+        jp = scb.choose_jparts(n_rb, ns, n_jb, 148)
+        assert 1 <= jp <= min(n_jb, 16)
+
+
+def test_uniformity_signatures_run():
+    from sparsify_clip_b200 import uniformity as u
+    x = torch.nn.functional.normalize(torch.randn(64, 16, dtype=torch.float64), dim=-1)
+    a = u.torch_uniformity1(x).item()
+    assert a == pytest.approx(u.torch_uniformity_equivalent(x).item(), rel=1e-5)
+    assert u.torch_uniformity(x, x).item() < 0 and u.numpy_uniformity(x, x) < 0
+    assert u.uniformity10(x).item() > 0
+
+
+# ----------------------------------------------------------------------------- sharded algebra (gloo, 2 ranks)
+def _worker(rank, world, port, I, T, tau, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    backend_cuda.set_backend(FakeBackend())
+    n = I.shape[0] // world
+    Il = I[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+    Tl = T[rank * n:(rank + 1) * n].clone().requires_grad_(True)
+    tp = torch.nn.Parameter(torch.tensor(tau, dtype=torch.float64))
+    w = dict(anchor=1.0, align=1.5, unif_img=0.5, unif_txt=0.25, unif_cen=0.7)
+    loss = scb.weighted_loss(Il, Tl, tp, w, group=True)
+    (loss * 2.0).backward()
+    out[rank] = (loss.item(), Il.grad.numpy() / 2.0, Tl.grad.numpy() / 2.0, tp.grad.item() / 2.0)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_two_ranks_match_full_batch_oracle():
+    g = torch.Generator().manual_seed(7)
+    B, D, tau = 24, 16, 0.2
+    I = torch.nn.functional.normalize(torch.randn(B, D, generator=g, dtype=torch.float64), dim=-1)
+    T = torch.nn.functional.normalize(I + 0.5 * torch.randn(B, D, generator=g, dtype=torch.float64), dim=-1)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, 29517 + os.getpid() % 1000, I, T, tau, out), nprocs=2, join=True)
+    ref_loss, dI, dT, dtau, _ = cf.weighted_loss(I.numpy(), T.numpy(), tau, 1.0, 1.5, 0.5, 0.25, 0.7)
+    n = B // 2
+    for r in (0, 1):
+        loss, gI, gT, gtau = out[r]
+        assert loss == pytest.approx(ref_loss, rel=1e-12)
+        assert np.abs(gI - dI[r * n:(r + 1) * n]).max() < 1e-7   # grad_output travels as fp32
+        assert np.abs(gT - dT[r * n:(r + 1) * n]).max() < 1e-7
+        assert gtau == pytest.approx(dtau, rel=1e-6)
+
+
+def test_single_process_fake_backend_matches_oracle():
+    prev = backend_cuda.set_backend(FakeBackend())
+    try:
+        g = torch.Generator().manual_seed(3)
+        I = torch.nn.functional.normalize(torch.randn(17, 8, generator=g, dtype=torch.float64), dim=-1).requires_grad_(True)
+        T = torch.nn.functional.normalize(torch.randn(17, 8, generator=g, dtype=torch.float64), dim=-1).requires_grad_(True)
+        cfg = {"loss_type": "only_lunif_n_then_anchor+ALPHA*lalign+BETA*lunif(centroids)", "only_lunif_epochs": 0,
+               "beta_warmup_epoch": 20, "beta_decay_epoch": 50, "alpha_warmup_epoch": 50, "alpha_increment_epoch": 50}
+        loss = scb.compose_loss(cfg, I, T, 0.1, epoch=3, current_batch=600, t_total=1000)
+        loss.backward()
+        ref_loss, dI, dT, _, _ = cf.compose_loss(cfg, I.detach().numpy(), T.detach().numpy(), 0.1, 3, 600, 1000)
+        assert loss.item() == pytest.approx(ref_loss, rel=1e-12)
+        assert np.abs(I.grad.numpy() - dI).max() < 1e-7 and np.abs(T.grad.numpy() - dT).max() < 1e-7
+    finally:
+        backend_cuda.set_backend(prev)
