@@ -81,7 +81,7 @@ class CudaBackend:
             return False
 
     # ------------------------------------------------------------------ tensor plumbing
-    def prep(self, x):
+    def prep(self, x, cast_fp32=True):
         if not isinstance(x, torch.Tensor) or x.dim() != 2:
             raise ValueError("expected a 2-D [B, D] tensor")
         if not x.is_cuda:
@@ -89,7 +89,7 @@ class CudaBackend:
         x = x.detach()
         if x.dtype not in _DT:
             x = x.float()
-        if x.dtype == torch.float32 and _fp32_mode == "bf16":
+        if x.dtype == torch.float32 and _fp32_mode == "bf16" and cast_fp32:
             x = x.to(torch.bfloat16)
         if x.stride(1) != 1 or x.stride(0) < x.shape[1]:
             x = x.contiguous()
@@ -101,6 +101,10 @@ class CudaBackend:
         for m in mats:
             if m.dtype == torch.float32 or m.shape[1] % 8 or m.stride(0) % 8 or m.data_ptr() % 16:
                 return PATH_SIMT
+        # below one 128-column tile the 16-bit weight tile is not averaged over enough pairs to stay inside
+        # the 1e-3 gradient gate (and a single CTA of fp32 FMAs is just as fast): exact path
+        if min(m.shape[0] for m in mats) < 128:
+            return PATH_SIMT
         return PATH_TC
 
     @staticmethod

@@ -9,6 +9,18 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of the (fully converged) warp; the compiler keeps warp-uniform operands in uniform registers
+// when the surrounding control flow is warp-uniform and only the async instruction is under this predicate.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -115,6 +127,12 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_byte
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
+// Split form for tight issue loops: hi word is a constant, lo word = start>>4 | LBO>>4 << 16.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO=1024, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo) { return ((uint64_t)kDescHiSw128 << 32) | (uint64_t)lo; }
 // K-major operand (rows = M or N index, 64 K-elements contiguous per row): SBO = 8 rows * 128 B.
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) { return desc_sw128(saddr, 16, 1024); }
 // MN-major operand (rows = K index, 64 MN-elements contiguous per row): SBO = 8 K-rows * 128 B,
@@ -123,8 +141,8 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t mn_blo
   return desc_sw128(saddr, mn_block_stride, 1024);
 }
 // Instruction descriptor for kind::f16, fp32 accumulate.  fmt: 1 = bf16, 0 = fp16.
-__device__ __host__ __forceinline__ uint32_t idesc_f16(int M, int N, int fmt, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
+__device__ __host__ __forceinline__ uint32_t idesc_f16(int M, int N, int afmt, int bfmt, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

@@ -29,15 +29,17 @@ enum { M_LSE = 0, M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2, M_LUNIF_SUM = 3, M_SPARSI
 
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
-constexpr int kSlotBytes = 128 * 64 * 2;  // one [128 x 64] 16-bit tile
-constexpr int kMaxStages = 14;
+constexpr int kSlotBytes = 128 * 64 * 2;  // one [128 x 64] 16-bit tile ("chunk")
+constexpr int kPairBytes = 2 * kSlotBytes; // ring unit: two chunks under one full / one empty barrier
+constexpr int kMaxStages = 7;              // pair-slots
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColOut = 0, kColS0 = 256;
 
 struct TcParams {
   int64_t nA, nB;
   int D, kch, nsplit, n_rb, n_jb, jparts;
-  int a_stationary, nstage, g_in_tmem, fmt;  // fmt: 1 bf16, 0 fp16
+  int a_stationary, nstage, g_in_tmem, fmt;  // fmt: 1 bf16, 0 fp16 (both MMA operands must share it:
+                                             // a mixed-format kind::f16 descriptor is an illegal instruction)
   float p0;                                  // LSE/anchor: scale*log2e ; lunif: t*log2e
   const float* rowvec;
   const float* colvec;
@@ -62,13 +64,12 @@ enum {
   BAR_COUNT
 };
 
+// Ring of `n` pair-slots.  `bits` holds the parity to wait for, per slot.
 struct Ring {
   uint32_t slot, bits;
-  __device__ __forceinline__ uint32_t take(int n, int nstage) {  // n contiguous slots, never wrapping
-    if (slot + n > (uint32_t)nstage) slot = 0;
+  __device__ __forceinline__ uint32_t take(uint32_t n) {
     const uint32_t s = slot;
-    slot += n;
-    if (slot >= (uint32_t)nstage) slot = 0;
+    slot = (slot + 1 == n) ? 0u : slot + 1;
     return s;
   }
   __device__ __forceinline__ uint32_t parity_then_flip(uint32_t s) {
@@ -78,7 +79,9 @@ struct Ring {
   }
 };
 
-template <int MODE>
+// KCH: number of 64-wide K chunks when known at compile time (8 for D = 512: the kc loops unroll and the
+// stationary-A descriptors become immediates), 0 = generic.
+template <int MODE, int KCH>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
   constexpr bool GRAD = (MODE == M_ANCHOR_GRAD || MODE == M_LUNIF_GRAD);
@@ -89,7 +92,10 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t a_bytes = P.a_stationary ? (uint32_t)P.kch * kSlotBytes : 0u;
   const uint32_t sm_a = smem_base;
   const uint32_t sm_ring = sm_a + a_bytes;
-  const uint32_t sm_g = sm_ring + (uint32_t)P.nstage * kSlotBytes;
+  const uint32_t sm_g = sm_ring + (uint32_t)P.nstage * kPairBytes;
+  const int kch = KCH ? KCH : P.kch;
+  const bool a_stat = KCH ? true : (P.a_stationary != 0);   // compile-time in the specialised kernels
+  const uint32_t nps = (uint32_t)P.nstage;
   const uint32_t g_bytes = (GRAD && !P.g_in_tmem) ? 2u * kSlotBytes : 0u;
   const uint32_t sm_cbuf = sm_g + g_bytes;            // 2 x 128 floats
   const uint32_t sm_bar = sm_cbuf + 1024u;            // BAR_COUNT x 8 bytes
@@ -127,134 +133,167 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t tmem_base = *tmem_ptr_slot;
 
   // =========================================================================== TMA producer
+  // The whole warp runs the (warp-uniform) control flow; one elected lane issues the async copies.
   if (warp == 0) {
-    if (lane == 0) {
-      Ring ring{0u, 0xFFFFFFFFu};
-      uint32_t a_empty_par = 1;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int split = item % nsplit_eff;
-        const int rb = (item / nsplit_eff) % P.n_rb;
-        const int jp = item / (nsplit_eff * P.n_rb);
-        const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
-        const int nt = jb_hi - jb_lo;
-        const int gch = min(4, P.kch - 4 * split);
-        if (P.a_stationary) {
-          ptx::mbar_wait(bar(BAR_A_EMPTY), a_empty_par, 100);
-          a_empty_par ^= 1;
-          ptx::mbar_expect_tx(bar(BAR_A_FULL), (uint32_t)P.kch * kSlotBytes);
-          for (int kc = 0; kc < P.kch; ++kc) ptx::tma_load_2d(sm_a + kc * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_A_FULL));
+    Ring ring{0u, 0xFFFFFFFFu};
+    uint32_t a_empty_par = 1;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int split = item % nsplit_eff;
+      const int rb = (item / nsplit_eff) % P.n_rb;
+      const int jp = item / (nsplit_eff * P.n_rb);
+      const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
+      const int nt = jb_hi - jb_lo;
+      const int gch = min(4, kch - 4 * split);
+      if (a_stat) {
+        ptx::mbar_wait(bar(BAR_A_EMPTY), a_empty_par, 100);
+        a_empty_par ^= 1;
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(bar(BAR_A_FULL), (uint32_t)kch * kSlotBytes);
+          for (int kc = 0; kc < kch; ++kc) ptx::tma_load_2d(sm_a + kc * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_A_FULL));
         }
-        auto load_b2 = [&](int tt) {
-          const uint32_t s0 = ring.take(gch, P.nstage);
-          for (int c = 0; c < gch; ++c) {
-            const uint32_t s = s0 + c;
-            ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), 110);
-            ptx::mbar_expect_tx(bar(BAR_FULL + s), kSlotBytes);
-            ptx::tma_load_2d(sm_ring + s * kSlotBytes, &tmB, (4 * split + c) * 64, (jb_lo + tt) * 128, bar(BAR_FULL + s));
-          }
-        };
-        for (int t = 0; t < nt; ++t) {
-          for (int kc = 0; kc < P.kch; ++kc) {
-            if (!P.a_stationary) {
-              const uint32_t s = ring.take(1, P.nstage);
-              ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), 120);
-              ptx::mbar_expect_tx(bar(BAR_FULL + s), kSlotBytes);
-              ptx::tma_load_2d(sm_ring + s * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_FULL + s));
-            }
-            const uint32_t s = ring.take(1, P.nstage);
-            ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), 121);
-            ptx::mbar_expect_tx(bar(BAR_FULL + s), kSlotBytes);
-            ptx::tma_load_2d(sm_ring + s * kSlotBytes, &tmB, kc * 64, (jb_lo + t) * 128, bar(BAR_FULL + s));
-          }
-          if (GRAD && t >= 1) load_b2(t - 1);
-        }
-        if (GRAD && nt > 0) load_b2(nt - 1);
+        __syncwarp();
       }
+      // one pair-slot: up to two [128 x 64] chunks (x = first column, consecutive 64-wide chunks) of rows y..y+127
+      auto load_pair = [&](const CUtensorMap* tm, int x, int y, int n, int tag) {
+        const uint32_t s = ring.take(nps);
+        ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), tag);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(bar(BAR_FULL + s), (uint32_t)n * kSlotBytes);
+          ptx::tma_load_2d(sm_ring + s * kPairBytes, tm, x, y, bar(BAR_FULL + s));
+          if (n > 1) ptx::tma_load_2d(sm_ring + s * kPairBytes + kSlotBytes, tm, x + 64, y, bar(BAR_FULL + s));
+        }
+        __syncwarp();
+      };
+      auto load_v = [&](int tt) {   // V tile of column block tt: <=2 pair-slots (128 output columns each)
+        for (int c0 = 0; c0 < gch; c0 += 2)
+          load_pair(&tmB, (4 * split + c0) * 64, (jb_lo + tt) * 128, min(2, gch - c0), 110);
+      };
+      for (int t = 0; t < nt; ++t) {
+        for (int kc = 0; kc < kch; kc += 2) {
+          if (!a_stat) load_pair(&tmA, kc * 64, rb * 128, min(2, kch - kc), 120);
+          load_pair(&tmB, kc * 64, (jb_lo + t) * 128, min(2, kch - kc), 121);
+        }
+        if (GRAD && t >= 1) load_v(t - 1);
+      }
+      if (GRAD && nt > 0) load_v(nt - 1);
     }
   }
   // =========================================================================== MMA issuer
+  // Converged warp; elect.sync picks the one lane that issues tcgen05.mma / tcgen05.commit.  Descriptor
+  // words are warp-uniform (uniform registers); the loop body is kept minimal because this single warp must
+  // issue 8 MMAs (512 tensor-pipe cycles) faster than the pipe retires them.
   else if (warp == 1) {
-    if (lane == 0) {
-      Ring ring{0u, 0u};
-      uint32_t a_full_par = 0, out_empty_par = 1;
-      uint32_t gt1 = 0, gt2 = 0;  // global tile counters of issued MMA1 / MMA2
-      const uint32_t idesc1 = ptx::idesc_f16(128, 128, P.fmt, 0, 0);
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int split = item % nsplit_eff;
-        const int jp = item / (nsplit_eff * P.n_rb);
-        const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
-        const int nt = jb_hi - jb_lo;
-        const int gch = min(4, P.kch - 4 * split);
-        const uint32_t idesc2 = ptx::idesc_f16(128, 64 * gch, P.fmt, 0, 1);
-        if (P.a_stationary) {
-          ptx::mbar_wait(bar(BAR_A_FULL), a_full_par, 200);
-          a_full_par ^= 1;
-        }
-        auto mma1 = [&](bool last) {
-          const uint32_t b = gt1 & 1u;
-          ptx::mbar_wait(bar(BAR_S_EMPTY + b), ((gt1 >> 1) & 1u) ^ 1u, 210);
+    Ring ring{0u, 0u};
+    uint32_t a_full_par = 0, out_empty_par = 1;
+    uint32_t gt1 = 0, gt2 = 0;  // global tile counters of issued MMA1 / MMA2
+    const uint32_t idesc1 = ptx::idesc_f16(128, 128, P.fmt, P.fmt, 0, 0);
+    const uint32_t a_lo0 = ptx::desc_lo(sm_a, 16);
+    const uint32_t ring_lo0 = ptx::desc_lo(sm_ring, 16);
+    const uint32_t ring_v_lo0 = ptx::desc_lo(sm_ring, kSlotBytes);   // same address, LBO = one chunk (MN-major V)
+    constexpr uint32_t kChunkLo = kSlotBytes >> 4, kPairLo = kPairBytes >> 4;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int split = item % nsplit_eff;
+      const int jp = item / (nsplit_eff * P.n_rb);
+      const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
+      const int nt = jb_hi - jb_lo;
+      const int gch = min(4, kch - 4 * split);
+      if (a_stat) {
+        ptx::mbar_wait(bar(BAR_A_FULL), a_full_par, 200);
+        a_full_par ^= 1;
+      }
+      auto mma1 = [&](bool last) {
+        const uint32_t b = gt1 & 1u;
+        ptx::mbar_wait(bar(BAR_S_EMPTY + b), ((gt1 >> 1) & 1u) ^ 1u, 210);
+        const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
+        auto kgroup = [&](int kc, int nk) {      // 8 MMAs (two 64-wide K chunks) behind one full-barrier wait
+          uint32_t alo, sa = 0;
+          if (a_stat) {
+            alo = a_lo0 + (uint32_t)kc * kChunkLo;
+          } else {
+            sa = ring.take(nps);
+            ptx::mbar_wait(bar(BAR_FULL + sa), ring.parity_then_flip(sa), 211);
+            alo = ring_lo0 + sa * kPairLo;
+          }
+          const uint32_t sb = ring.take(nps);
+          ptx::mbar_wait(bar(BAR_FULL + sb), ring.parity_then_flip(sb), 212);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
-          for (int kc = 0; kc < P.kch; ++kc) {
-            uint32_t a_addr, sa = 0;
-            if (P.a_stationary) {
-              a_addr = sm_a + kc * kSlotBytes;
-            } else {
-              sa = ring.take(1, P.nstage);
-              ptx::mbar_wait(bar(BAR_FULL + sa), ring.parity_then_flip(sa), 211);
-              a_addr = sm_ring + sa * kSlotBytes;
-            }
-            const uint32_t sb = ring.take(1, P.nstage);
-            ptx::mbar_wait(bar(BAR_FULL + sb), ring.parity_then_flip(sb), 212);
-            ptx::tc_fence_after();
-            const uint32_t b_addr = sm_ring + sb * kSlotBytes;
+          const uint32_t blo = ring_lo0 + sb * kPairLo;
+          if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_ss(d_tmem, ptx::desc_kmajor(a_addr + k * 32), ptx::desc_kmajor(b_addr + k * 32), idesc1,
-                           (uint32_t)((kc | k) != 0));
-            if (!P.a_stationary) ptx::umma_commit(bar(BAR_EMPTY + sa));
+            for (uint32_t i = 0; i < 2; ++i) {
+              if ((int)i < nk) {
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)   // +32 B per K=16 step inside the 128B-swizzled row; +16 KB per chunk
+                  ptx::umma_ss(d_tmem, ptx::desc_join(alo + i * kChunkLo + 2u * k), ptx::desc_join(blo + i * kChunkLo + 2u * k),
+                               idesc1, (uint32_t)((kc | (int)i | (int)k) != 0));
+              }
+            }
+            if (!a_stat) ptx::umma_commit(bar(BAR_EMPTY + sa));
             ptx::umma_commit(bar(BAR_EMPTY + sb));
           }
-          ptx::umma_commit(bar(BAR_S_FULL + b));
-          if (last && P.a_stationary) ptx::umma_commit(bar(BAR_A_EMPTY));
-          ++gt1;
+          __syncwarp();
         };
-        auto mma2 = [&](bool first, bool last) {
-          const uint32_t b = gt2 & 1u;
-          ptx::mbar_wait(bar(BAR_G_FULL), gt2 & 1u, 220);
-          if (first) {
-            ptx::mbar_wait(bar(BAR_OUT_EMPTY), out_empty_par, 221);
-            out_empty_par ^= 1;
-          }
-          const uint32_t s0 = ring.take(gch, P.nstage);
-          for (int c = 0; c < gch; ++c) ptx::mbar_wait(bar(BAR_FULL + s0 + c), ring.parity_then_flip(s0 + c), 222);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + kColOut;
-          const uint32_t v_addr = sm_ring + s0 * kSlotBytes;
+        if constexpr (KCH > 0) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t bdesc = ptx::desc_mnmajor(v_addr + ks * 2048, kSlotBytes);
-            const uint32_t accum = (uint32_t)!(first && ks == 0);
-            if (P.g_in_tmem) {
-              const uint32_t a_tmem = tmem_base + kColS0 + 128u * b + (uint32_t)(ks >> 2) * 64u + (uint32_t)(ks & 3) * 8u;
-              ptx::umma_ts(d_tmem, a_tmem, bdesc, idesc2, accum);
-            } else {
-              const uint64_t adesc = ptx::desc_kmajor(sm_g + (uint32_t)(ks >> 2) * kSlotBytes + (uint32_t)(ks & 3) * 32u);
-              ptx::umma_ss(d_tmem, adesc, bdesc, idesc2, accum);
+          for (int kc = 0; kc < KCH; kc += 2) kgroup(kc, 2);
+        } else {
+#pragma unroll 1
+          for (int kc = 0; kc < kch; kc += 2) kgroup(kc, min(2, kch - kc));
+        }
+        if (ptx::elect_one()) {
+          ptx::umma_commit(bar(BAR_S_FULL + b));
+          if (last && a_stat) ptx::umma_commit(bar(BAR_A_EMPTY));
+        }
+        __syncwarp();
+        ++gt1;
+      };
+      auto mma2 = [&](bool first, bool last) {
+        const uint32_t b = gt2 & 1u;
+        ptx::mbar_wait(bar(BAR_G_FULL), gt2 & 1u, 220);
+        if (first) {
+          ptx::mbar_wait(bar(BAR_OUT_EMPTY), out_empty_par, 221);
+          out_empty_par ^= 1;
+        }
+        const uint32_t g_tmem = tmem_base + kColS0 + 128u * b;
+        const uint32_t glo = ptx::desc_lo(sm_g, 16);
+#pragma unroll
+        for (int c0 = 0; c0 < 4; c0 += 2) {      // output columns [64 c0, 64 c0 + 64 n) of this group
+          if (c0 >= gch) break;
+          const int n = min(2, gch - c0);
+          const uint32_t sv = ring.take(nps);
+          ptx::mbar_wait(bar(BAR_FULL + sv), ring.parity_then_flip(sv), 222);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + kColOut + 64u * (uint32_t)c0;
+          const uint32_t idesc2 = ptx::idesc_f16(128, 64 * n, P.fmt, P.fmt, 0, 1);
+          // V tile re-read as an MN-major operand: +2048 B (16 K-rows) per step, 64-wide blocks one chunk apart
+          const uint32_t vlo = ring_v_lo0 + sv * kPairLo;
+          const bool last_group = (c0 + 2 >= gch);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < 8; ++ks) {
+              const uint64_t bdesc = ptx::desc_join(vlo + 128u * ks);
+              const uint32_t accum = (uint32_t)!(first && ks == 0);
+              if (P.g_in_tmem)
+                ptx::umma_ts(d_tmem, g_tmem + (ks >> 2) * 64u + (ks & 3u) * 8u, bdesc, idesc2, accum);
+              else
+                ptx::umma_ss(d_tmem, ptx::desc_join(glo + (ks >> 2) * kChunkLo + (ks & 3u) * 2u), bdesc, idesc2, accum);
+            }
+            ptx::umma_commit(bar(BAR_EMPTY + sv));
+            if (last_group) {
+              if (P.g_in_tmem) ptx::umma_commit(bar(BAR_S_EMPTY + b));
+              else ptx::umma_commit(bar(BAR_G_EMPTY));
+              if (last) ptx::umma_commit(bar(BAR_OUT_FULL));
             }
           }
-          for (int c = 0; c < gch; ++c) ptx::umma_commit(bar(BAR_EMPTY + s0 + c));
-          if (P.g_in_tmem) ptx::umma_commit(bar(BAR_S_EMPTY + b));
-          else ptx::umma_commit(bar(BAR_G_EMPTY));
-          if (last) ptx::umma_commit(bar(BAR_OUT_FULL));
-          ++gt2;
-        };
-        for (int t = 0; t < nt; ++t) {
-          mma1(t == nt - 1);
-          if (GRAD && t >= 1) mma2(t == 1, false);
+          __syncwarp();
         }
-        if (GRAD && nt > 0) mma2(nt == 1, true);
+        ++gt2;
+      };
+      for (int t = 0; t < nt; ++t) {
+        mma1(t == nt - 1);
+        if (GRAD && t >= 1) mma2(t == 1, false);
       }
+      if (GRAD && nt > 0) mma2(nt == 1, true);
     }
   }
   // =========================================================================== epilogue warps
@@ -271,7 +310,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int jp = item / (nsplit_eff * P.n_rb);
       const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
       const int nt = jb_hi - jb_lo;
-      const int gch = min(4, P.kch - 4 * split);
+      const int gch = min(4, kch - 4 * split);
       const int64_t gi = (int64_t)rb * 128 + rrow;
       const bool row_ok = gi < P.nA;
       // per-row constants and running statistics
@@ -310,14 +349,19 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           ptx::tmem_ld_wait();
           const int64_t cbase = col0 + 32 * cc;
           const float* cb = cbuf + b * 128 + 64 * h + 32 * cc;
+          const int dcol = diag_here ? (int)(my_diag_col - cbase) : -1;   // local index of the diagonal, if any
+          // column tail (last column block only): neutralise the zero-filled columns once, up front
+          if (tile_partial && MODE != M_LUNIF_GRAD && MODE != M_LUNIF_SUM) {
+            const int nvalid = (int)min((int64_t)32, max((int64_t)0, P.nB - cbase));
+            const float dead = (MODE == M_LSE) ? -INFINITY : -1e30f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c >= nvalid) v[c] = __float_as_uint(dead);
+          }
           if (MODE == M_LSE) {
             float cmax = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float g = __uint_as_float(v[c]);
-              if (tile_partial && (cbase + c) >= P.nB) { g = -INFINITY; v[c] = __float_as_uint(g); }
-              cmax = fmaxf(cmax, g);
-            }
+            for (int c = 0; c < 32; ++c) cmax = fmaxf(cmax, __uint_as_float(v[c]));
             if (cmax != -INFINITY) {
               const float mnew = fmaxf(st0, cmax * P.p0);
               float sum = 0.f;
@@ -327,12 +371,16 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               st0 = mnew;
             }
           } else if (MODE == M_SPARSIFY_SUM) {
+            if (!tile_partial && !diag_here) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float g = __uint_as_float(v[c]);
-              const float er = g - ((diag_here && (cbase + c) == my_diag_col) ? 1.f : -1.f);
-              const bool ok = !tile_partial || (cbase + c) < P.nB;
-              st0 += ok ? er * er : 0.f;
+              for (int c = 0; c < 32; ++c) { const float er = __uint_as_float(v[c]) + 1.f; st0 = fmaf(er, er, st0); }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const float g = __uint_as_float(v[c]);
+                const float er = g - ((c == dcol) ? 1.f : -1.f);
+                st0 += (g > -1e29f) ? er * er : 0.f;
+              }
             }
           } else {
             float w[32];
@@ -341,12 +389,11 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               for (int c = 0; c < 32; ++c) {
                 const float g = __uint_as_float(v[c]);
                 const float y = g * P.p0;
-                float ww = scb_ex2(y - rowc) + scb_ex2(y - cb[c]);
-                if (tile_partial && (cbase + c) >= P.nB) ww = 0.f;
+                const float ww = scb_ex2(y - rowc) + scb_ex2(y - cb[c]);   // dead columns: 0 + 0
                 st0 = fmaf(ww, g, st0);
                 w[c] = ww;
               }
-            } else {  // lunif: exp2(2 p0 g - p0 n_i - p0 n_j); invalid columns carry +inf in cb -> 0
+            } else {  // lunif: exp2(2 p0 g - p0 n_i - p0 n_j); dead columns carry +inf in cb -> 0
               const float two_p0 = 2.f * P.p0;
 #pragma unroll
               for (int c = 0; c < 32; ++c) w[c] = scb_ex2(fmaf(__uint_as_float(v[c]), two_p0, -(rowc + cb[c])));
@@ -354,7 +401,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (diag_here) {
 #pragma unroll
               for (int c = 0; c < 32; ++c)
-                if ((cbase + c) == my_diag_col) w[c] = 0.f;
+                if (c == dcol) w[c] = 0.f;
             }
             if (MODE == M_LUNIF_SUM) {
 #pragma unroll
@@ -487,7 +534,7 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld,
   return 0;
 }
 
-int g_tc_flags = 0;
+int g_tc_flags = 1;   // bit0: weight tile in TMEM (TS-mode MMA2) -- measured faster than the smem variant
 
 template <int MODE>
 int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
@@ -509,11 +556,11 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
   P.a_stationary = (P.kch <= 8) ? 1 : 0;
   const int budget = 232448 - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
   const int fixed = (P.a_stationary ? P.kch * kSlotBytes : 0) + ((GRAD && !P.g_in_tmem) ? 2 * kSlotBytes : 0);
-  int nstage = (budget - fixed) / kSlotBytes;
+  int nstage = (budget - fixed) / kPairBytes;      // pair-slots of 32 KB
   if (nstage > kMaxStages) nstage = kMaxStages;
-  SCB_CHECK_ARG(nstage >= 4, SCB_E_SHAPE, "not enough shared memory for the tile ring (D=%d)", D);
+  SCB_CHECK_ARG(nstage >= 2, SCB_E_SHAPE, "not enough shared memory for the tile ring (D=%d)", D);
   P.nstage = nstage;
-  const size_t smem = (size_t)fixed + (size_t)nstage * kSlotBytes + 3 * 1024;
+  const size_t smem = (size_t)fixed + (size_t)nstage * kPairBytes + 3 * 1024;
 
   CUtensorMap tmA, tmB;
   int rc = make_tmap(&tmA, A, nA, D, ldA, dtype);
@@ -529,13 +576,15 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_pass<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_pass<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_pass<MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) { scb_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
   const int n_items = P.n_rb * (GRAD ? P.nsplit : 1) * P.jparts;
   const int grid = n_items < num_sms ? n_items : num_sms;
-  k_tc_pass<MODE><<<grid, kThreads, smem, s>>>(tmA, tmB, P);
+  if (P.kch == 8) k_tc_pass<MODE, 8><<<grid, kThreads, smem, s>>>(tmA, tmB, P);
+  else k_tc_pass<MODE, 0><<<grid, kThreads, smem, s>>>(tmA, tmB, P);
   SCB_CHECK_LAUNCH("tc_pass");
   return 0;
 }

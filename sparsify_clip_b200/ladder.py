@@ -10,7 +10,7 @@ get_alpha).  Behaviour is reproduced AS CODED:
     centroid variant is available as loss_type "...BETA*lunif(centroids)[intended]".
   * an unknown loss_type is an error (the reference dies at loss.item() one line later).
 """
-from .losses import contrastive_loss, lalign_loss, lunif_loss, normalized_centroids
+from .losses import contrastive_loss, lalign_loss, lunif_loss, normalized_centroids, centroid_operand_dtype
 
 __all__ = ["get_beta", "get_alpha", "ladder_weights", "compose_loss", "weighted_loss", "LOSS_TYPES"]
 
@@ -93,7 +93,8 @@ def weighted_loss(image_embeds, text_embeds, temperature, w, *, group=None):
     if w["unif_txt"] != 0.0:
         loss = add(loss, w["unif_txt"], lunif_loss(text_embeds, group=group))
     if w["unif_cen"] != 0.0:
-        loss = add(loss, w["unif_cen"], lunif_loss(normalized_centroids(image_embeds, text_embeds), group=group))
+        loss = add(loss, w["unif_cen"], lunif_loss(normalized_centroids(image_embeds, text_embeds), group=group,
+                                                   mma_dtype=centroid_operand_dtype(image_embeds)))
     if loss is None:
         loss = image_embeds.sum() * 0.0
     return loss

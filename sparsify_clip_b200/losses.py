@@ -24,7 +24,7 @@ from .backend_cuda import get_backend
 __all__ = [
     "contrastive_loss", "lunif_loss", "lalign_loss", "compute_centroids_only", "compute_centroids",
     "sparsify_loss", "random_alignment_loss", "contrastive_loss_roberta", "centroid_alignment_loss",
-    "normalized_centroids", "l2_normalize",
+    "normalized_centroids", "l2_normalize", "operand_dtype", "centroid_operand_dtype",
 ]
 
 
@@ -138,14 +138,18 @@ class _LunifFn(torch.autograd.Function):
     Gram tile); backward is one element-wise multiply by grad_output."""
 
     @staticmethod
-    def forward(ctx, x, t, group):
+    def forward(ctx, x, t, group, mma_dtype):
         be = get_backend()
-        xp = be.prep(x)
+        xp = be.prep(x, cast_fp32=mma_dtype is None)
+        # `mma_dtype`: dtype of the tensor-core operand when x is a higher-precision intermediate (the
+        # normalised centroids).  Distances are exact for the ROUNDED points; the x_i (sum_j w_ij) term of
+        # the gradient uses the unrounded rows, so the large radial component cancels exactly downstream.
+        xq = xp.to(mma_dtype) if (mma_dtype is not None and xp.dtype != mma_dtype) else xp
         rank, ws = _world(group)
         n = xp.shape[0]
-        x_all = _all_gather_rows(xp, group)
+        x_all = _all_gather_rows(xq, group)
         need = ctx.needs_input_grad[0]
-        core = be.lunif_core(xp, x_all, float(t), rank * n, need)
+        core = be.lunif_core(xq, x_all, float(t), rank * n, need)
         rs = _all_reduce_(core["rs_sum"], group)
         B = n * ws
         ssum = rs * 0.5
@@ -160,11 +164,11 @@ class _LunifFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         (gx,) = ctx.saved_tensors
-        return (gx * _gout32(gout)).to(ctx.in_dtype), None, None
+        return (gx * _gout32(gout)).to(ctx.in_dtype), None, None, None
 
 
-def lunif_loss(x, t=2, *, group=None):
-    return _LunifFn.apply(x, t, _resolve_group(group))
+def lunif_loss(x, t=2, *, group=None, mma_dtype=None):
+    return _LunifFn.apply(x, t, _resolve_group(group), mma_dtype)
 
 
 # ----------------------------------------------------------------------------- L_align
@@ -208,7 +212,7 @@ class _CentroidFn(torch.autograd.Function):
         be = get_backend()
         a, b = _common(a, b)
         ap, bp = be.prep(a), be.prep(b)
-        C, inv = be.centroid_fwd(ap, bp, ap.dtype)
+        C, inv = be.centroid_fwd(ap, bp, torch.float32)     # fp32 master copy (see lunif_loss(mma_dtype=...))
         ctx.in_dtypes = (a.dtype, b.dtype)
         ctx.save_for_backward(ap, bp, inv)
         return C
@@ -222,8 +226,23 @@ class _CentroidFn(torch.autograd.Function):
 
 
 def normalized_centroids(a, b):
-    """F.normalize(compute_centroids_only(a, b), dim=-1) in one kernel (forward and backward)."""
+    """F.normalize(compute_centroids_only(a, b), dim=-1) in one kernel (forward and backward).
+    Returns fp32; pass ``mma_dtype=operand_dtype(a)`` to lunif_loss to keep it on the tensor-core path."""
     return _CentroidFn.apply(a, b)
+
+
+def centroid_operand_dtype(x):
+    """Tensor-core operand dtype for normalize((I+T)/2) given what I is computed in.  The centroid is an
+    fp32 intermediate, not an input: when I/T run on the tensor cores it is handed over as fp16 (11-bit
+    mantissa; components of a unit vector are far inside fp16's range), which keeps L_unif(centroids)
+    within the 1e-5 / 1e-3 parity gates where a bf16 operand (8 bits) does not."""
+    d = operand_dtype(x)
+    return torch.float16 if d in (torch.bfloat16, torch.float16) else d
+
+
+def operand_dtype(x):
+    """dtype the B x B passes will use for `x` (bf16/fp16 stay; fp32 -> bf16 under set_fp32_mode('bf16'))."""
+    return get_backend().prep(x[:1]).dtype
 
 
 class _NormalizeFn(torch.autograd.Function):

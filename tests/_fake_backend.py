@@ -10,8 +10,11 @@ class FakeBackend:
     launches = 0
     pass_events = None
 
-    def prep(self, x):
+    def prep(self, x, cast_fp32=True):
         return x.detach().double().contiguous()
+
+    def path_for(self, *mats):
+        return 0
 
     def sum(self, x):
         return x.double().sum()

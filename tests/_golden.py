@@ -24,7 +24,7 @@ def load(name):
     return z
 
 
-def grad_check(z, key, got, rtol):
+def grad_check(z, key, got, rtol, row_factor=1.0):
     """Compare a full gradient `got` [B,D] against golden `f64_<key>` (full or sampled rows)."""
     got = np.asarray(got, dtype=np.float64)
     if "f64_" + key in z:
@@ -37,7 +37,7 @@ def grad_check(z, key, got, rtol):
     fro = float(z["f64_" + key + "_fro"])
     scale = fro / np.sqrt(got.shape[0])          # typical row norm
     err_rows = np.linalg.norm(got[rows] - ref_rows, axis=1) / max(scale, 1e-30)
-    assert err_rows.max() <= rtol, f"{z['name']}:{key} sampled-row err {err_rows.max():.3e} > {rtol}"
+    assert err_rows.max() <= rtol * row_factor, f"{z['name']}:{key} sampled-row err {err_rows.max():.3e} > {rtol * row_factor}"
     err_fro = abs(np.linalg.norm(got) - fro) / max(fro, 1e-30)
     assert err_fro <= rtol, f"{z['name']}:{key} fro-norm err {err_fro:.3e} > {rtol}"
     return max(err_rows.max(), err_fro)

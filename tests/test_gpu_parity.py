@@ -51,7 +51,7 @@ def _run_terms(I, T, tau, gscale=1.0):
     ut = scb.lunif_loss(T)
     out["lunif_txt"] = ut.item()
     (out["lunif_txt_dX"],) = grads(ut, T)
-    uc = scb.lunif_loss(scb.normalized_centroids(I, T))
+    uc = scb.lunif_loss(scb.normalized_centroids(I, T), mma_dtype=scb.centroid_operand_dtype(I))
     out["lunif_cen"] = uc.item()
     out["lunif_cen_dI"], out["lunif_cen_dT"] = grads(uc, I, T)
     w3 = dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0)
@@ -62,15 +62,18 @@ def _run_terms(I, T, tau, gscale=1.0):
     return out
 
 
-def _check_against(z, got, loss_rtol, grad_rtol, cen_loss_rtol=None):
-    for k in ("anchor", "lalign", "lunif_img", "lunif_txt", "exp3"):
+def _check_against(z, got, loss_rtol, grad_rtol, cen_loss_rtol=None, row_factor=1.0):
+    for k in ("anchor", "lalign", "lunif_img", "lunif_txt"):
         assert _rel(got[k], float(z["f64_" + k])) <= loss_rtol, (z["name"], k, got[k], float(z["f64_" + k]))
+    mag = abs(float(z["f64_anchor"])) + abs(float(z["f64_lalign"])) + 0.5 * abs(float(z["f64_lunif_img"])) + \
+        0.5 * abs(float(z["f64_lunif_txt"]))
+    assert abs(got["exp3"] - float(z["f64_exp3"])) <= loss_rtol * mag, (z["name"], "exp3")
     assert _rel(got["lunif_cen"], float(z["f64_lunif_cen"])) <= (cen_loss_rtol or loss_rtol), (z["name"], "lunif_cen")
     for k in ("anchor_dtau", "exp3_dtau"):
         assert _rel(got[k], float(z["f64_" + k])) <= max(grad_rtol, 1e-5), (z["name"], k, got[k], float(z["f64_" + k]))
     for k in ("anchor_dI", "anchor_dT", "lalign_dI", "lalign_dT", "lunif_img_dX", "lunif_txt_dX", "lunif_cen_dI",
               "lunif_cen_dT", "exp3_dI", "exp3_dT"):
-        _golden.grad_check(z, k, got[k], grad_rtol)
+        _golden.grad_check(z, k, got[k], grad_rtol, row_factor)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -83,7 +86,7 @@ def test_fp32_exact_path_matches_golden(name):
 
 
 @pytest.mark.parametrize("tc_flags", [0, 1])
-@pytest.mark.parametrize("name", [n for n in CASES if "bf16" in n or "tau001" in n or "nonunit" in n or "b129_d64_corr" in n])
+@pytest.mark.parametrize("name", [n for n in CASES if bool(_golden.load(n)["bf16_exact"])])
 def test_bf16_tensor_core_path_matches_golden(name, tc_flags):
     """bf16-exact inputs -> TMA + tcgen05 kernels.  Inputs are handed over as fp32 tensors holding bf16-exact
     values with fp32 mode 'bf16', so the returned gradients are fp32 (not re-rounded to bf16)."""
@@ -97,8 +100,10 @@ def test_bf16_tensor_core_path_matches_golden(name, tc_flags):
     finally:
         scb.set_fp32_mode(prev)
         be.lib.scb_set_tc_flags(prev_flags)
-    # the centroid operand is itself rounded to bf16 before the Gram tile: documented 1e-4 on that one loss
-    _check_against(z, got, LOSS_RTOL, GRAD_RTOL["bf16"], cen_loss_rtol=1e-4)
+    # the gate is norm-wise (1e-3 of the gradient's Frobenius norm); fixtures that only store sampled rows
+    # additionally bound every sampled row by 2e-3 of the typical row norm (peaky tau=0.01 rows do not
+    # average the 2^-9 rounding of the weight tile over many pairs)
+    _check_against(z, got, LOSS_RTOL, GRAD_RTOL["bf16"], row_factor=2.0)
 
 
 @pytest.mark.parametrize("B,D,tau,kind", [(127, 512, 0.1, "corr"), (129, 1024, 0.07, "cluster"), (1000, 64, 1.0, "corr"),
@@ -116,8 +121,9 @@ def test_tensor_core_path_vs_oracle_on_seeded_inputs(B, D, tau, kind):
         loss.backward()
     finally:
         scb.set_fp32_mode(prev)
-    ref, dI, dT, dtau, _ = cf.weighted_loss(I.numpy(), T.numpy(), tau, 1.0, 1.0, 0.5, 0.5, 0.0)
-    assert _rel(loss.item(), ref) <= LOSS_RTOL
+    ref, dI, dT, dtau, terms = cf.weighted_loss(I.numpy(), T.numpy(), tau, 1.0, 1.0, 0.5, 0.5, 0.0)
+    # the composite can cancel to ~0: 1e-5 relative to the magnitude of its terms
+    assert abs(loss.item() - ref) <= LOSS_RTOL * sum(abs(v) for v in terms.values())
     assert np.linalg.norm(Ig.grad.double().cpu().numpy() - dI) / np.linalg.norm(dI) <= 1e-3
     assert np.linalg.norm(Tg.grad.double().cpu().numpy() - dT) / np.linalg.norm(dT) <= 1e-3
     assert _rel(tp.grad.item(), dtau) <= 1e-3
@@ -213,6 +219,6 @@ def test_ladder_on_gpu_matches_oracle():
             Ig, Tg = I.cuda().requires_grad_(True), T.cuda().requires_grad_(True)
             loss = scb.compose_loss(cfg, Ig, Tg, 0.1, epoch=epoch, current_batch=step, t_total=1000)
             loss.backward()
-            ref, dI, dT, _, _ = cf.compose_loss(cfg, I.numpy(), T.numpy(), 0.1, epoch, step, 1000)
-            assert _rel(loss.item(), ref) <= LOSS_RTOL, (lt, epoch)
+            ref, dI, dT, _, terms = cf.compose_loss(cfg, I.numpy(), T.numpy(), 0.1, epoch, step, 1000)
+            assert abs(loss.item() - ref) <= LOSS_RTOL * sum(abs(v) for v in terms.values()), (lt, epoch)
             assert np.linalg.norm(Ig.grad.double().cpu().numpy() - dI) <= 1e-5 * max(np.linalg.norm(dI), 1e-30), (lt, epoch)
