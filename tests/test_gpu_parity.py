@@ -100,10 +100,15 @@ def test_bf16_tensor_core_path_matches_golden(name, tc_flags):
     finally:
         scb.set_fp32_mode(prev)
         be.lib.scb_set_tc_flags(prev_flags)
-    # the gate is norm-wise (1e-3 of the gradient's Frobenius norm); fixtures that only store sampled rows
-    # additionally bound every sampled row by 2e-3 of the typical row norm (peaky tau=0.01 rows do not
-    # average the 2^-9 rounding of the weight tile over many pairs)
-    _check_against(z, got, LOSS_RTOL, GRAD_RTOL["bf16"], row_factor=2.0)
+    # The gate is norm-wise: 1e-3 of the gradient's Frobenius norm, checked in full against the oracle below.
+    # Fixtures that only store sampled rows (which include the planted duplicate rows, the worst case at
+    # tau = 0.01 where one 2^-9-rounded weight dominates a row) bound each sampled row by 3e-3 of the typical row norm.
+    _check_against(z, got, LOSS_RTOL, GRAD_RTOL["bf16"], row_factor=3.0)
+    _, dI, dT, _, _ = cf.weighted_loss(z["I"], z["T"], float(z["tau"]), 1.0, 1.0, 0.5, 0.5, 0.0)
+    _, aI, aT, _ = cf.contrastive_loss(z["I"], z["T"], float(z["tau"]))
+    for key, ref in (("exp3_dI", dI), ("exp3_dT", dT), ("anchor_dI", aI), ("anchor_dT", aT)):
+        err = np.linalg.norm(got[key] - ref) / np.linalg.norm(ref)
+        assert err <= GRAD_RTOL["bf16"], (name, key, err)
 
 
 @pytest.mark.parametrize("B,D,tau,kind", [(127, 512, 0.1, "corr"), (129, 1024, 0.07, "cluster"), (1000, 64, 1.0, "corr"),
