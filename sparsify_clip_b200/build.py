@@ -1,4 +1,4 @@
-"""Build libscb200.so in-tree with nvcc for sm_100a (no torch headers: the library is plain C ABI)."""
+"""Build libscb200.so in-tree with nvcc for sm_100a (no torch headers: the library is a plain C ABI)."""
 import os
 import shutil
 import subprocess
@@ -9,6 +9,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscb200.so")
 SOURCES = ["rowwise.cu", "simt_pass.cu", "tc_pass.cu", "api.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "scb200.h")]
+# no --use_fast_math: the SIMT path is the exact fp32 path (expf/exp2f/division must stay IEEE-accurate)
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+         "-Wno-deprecated-gpu-targets"]
 
 
 def _nvcc():
@@ -22,8 +25,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in SOURCES + HEADERS)
 
 
 def build(force=False, verbose=False):
@@ -31,27 +33,23 @@ def build(force=False, verbose=False):
         return LIB
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-             "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3"]
-    # --use_fast_math would turn expf/exp2f/division into approximations in the exact SIMT path:
-    flags.remove("--use_fast_math")
-    procs = []
-    objs = []
-    for s in SOURCES:
-        o = os.path.join(objdir, s.replace(".cu", ".o"))
-        objs.append(o)
-        procs.append((s, subprocess.Popen([_nvcc(), *flags, "-c", os.path.join(CSRC, s), "-o", o],
-                                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    fail = False
-    for s, p in procs:
+    flags = FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    procs, objs = [], []
+    for src in SOURCES:            # one nvcc per translation unit, in parallel
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode:
-            sys.stderr.write(f"--- nvcc {s}\n{out}\n")
-        fail |= p.returncode != 0
-    if fail:
+            sys.stderr.write(f"--- nvcc {src}\n{out}\n")
+        failed |= p.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB + ".tmp", *objs, "-lcuda" if False else "-lcudart_static",
-                           "-lpthread", "-ldl", "-lrt"])
+    subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB + ".tmp", *objs,
+                           "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     os.replace(LIB + ".tmp", LIB)
     return LIB
 
