@@ -24,8 +24,8 @@
  *  - "jparts": the column sweep of a pass may be split into `jparts` contiguous parts so
  *    that the grid fills 148 SMs; each part writes its own partial result and the
  *    *_finalize / *_combine entry points add the partials in a fixed order
- *    (deterministic, no float atomics).  A pass writes nsub = scb_pass_nsub(path)
- *    sub-partials per part for the per-row statistics.
+ *    (deterministic, no float atomics).  A pass writes nsub sub-partials per part
+ *    for the per-row statistics (scb_pass_plan reports jparts and nsub).
  */
 #ifndef SCB200_H_
 #define SCB200_H_
@@ -50,10 +50,14 @@ extern "C" {
 
 int scb_version(void);
 const char* scb_last_error(void);
-/* number of per-row statistic sub-partials each column part writes (1 SIMT, 2 TC) */
-int scb_pass_nsub(int path);
-/* debug/tuning knobs for the TC path: bit0 = keep the weight tile in TMEM (TS-mode MMA)
- * instead of shared memory.  Returns the previous value. */
+/* Launch plan of a B x B pass with nA rows against nB columns (host-only arithmetic, no CUDA call):
+ * *jparts = how many contiguous parts the column sweep is split into so that the work items fill
+ * n_sm SMs evenly; *nsub = per-row statistic sub-partials each part writes (1 SIMT, 2 TC, 4 TC on a
+ * CTA pair).  grad != 0 for the passes that also produce a [nA, D] output. */
+int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, int n_sm, int* jparts, int* nsub);
+/* debug/tuning knobs for the TC path: bit0 = keep the weight tile in TMEM (TS-mode MMA) instead of
+ * shared memory; bit1 = run the gradient passes on CTA pairs (cluster of 2, weight tile shared through
+ * distributed shared memory) when 256 < D <= 512.  Returns the previous value. */
 int scb_set_tc_flags(int flags);
 
 /* ------------------------------------------------------------------ row-wise kernels */

@@ -19,7 +19,7 @@ _vp, _i64, _i32, _f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_
 # name -> argtypes, in the order of include/scb200.h
 SIGNATURES = {
     "scb_version": [],
-    "scb_pass_nsub": [_i32],
+    "scb_pass_plan": [_i32, _i64, _i64, _i32, _i32, _i32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)],
     "scb_set_tc_flags": [_i32],
     "scb_row_sqnorm": [_vp, _i64, _i32, _i64, _i32, _vp, _vp],
     "scb_row_dot": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _vp],

@@ -3,6 +3,7 @@
 PyTorch is only plumbing here: it owns the device buffers and the stream.  All arithmetic
 on the hot path happens in the library's kernels.
 """
+import ctypes
 import math
 
 import torch
@@ -36,6 +37,8 @@ def choose_jparts(n_rb, nsplit, n_jb, n_sm=148, max_parts=16):
     """Split the column sweep so that (row blocks x column groups x parts) fills the SMs evenly.
 
     cost model: rounds of `n_sm` concurrent work items x (tiles per item + 1 tile of prologue/drain).
+    Host mirror of the planner inside the library (scb_pass_plan, csrc/api.cu), which is the one the
+    backend uses; tests/test_host.py checks that the two agree.
     """
     best, best_cost = 1, None
     for jp in range(1, max(1, min(n_jb, max_parts)) + 1):
@@ -114,12 +117,12 @@ class CudaBackend:
     def _n_sm(self, dev):
         return torch.cuda.get_device_properties(dev).multi_processor_count
 
-    def _jparts(self, path, nA, nB, D, grad, dev):
-        if path == PATH_TC:
-            kch = (D + 63) // 64
-            return choose_jparts((nA + 127) // 128, (kch + 3) // 4 if grad else 1, (nB + 127) // 128, self._n_sm(dev))
-        tiles = ((nA + 31) // 32) * (((D + 127) // 128) if grad else 1)
-        return max(1, min((nB + 31) // 32, (2 * self._n_sm(dev)) // max(tiles, 1)))
+    def _plan(self, path, nA, nB, D, grad, dev):
+        """(jparts, nsub) of one B x B pass, from the library's planner."""
+        jp, nsub = ctypes.c_int(0), ctypes.c_int(0)
+        check(self.lib.scb_pass_plan(path, nA, nB, D, int(bool(grad)), self._n_sm(dev), ctypes.byref(jp),
+                                     ctypes.byref(nsub)), "pass_plan")
+        return jp.value, nsub.value
 
     def sum(self, x):
         x = x.contiguous().view(-1)
@@ -211,8 +214,7 @@ class CudaBackend:
         nA, D = A.shape
         nB = Ball.shape[0]
         path = self.path_for(A, Ball)
-        jp = self._jparts(path, nA, nB, D, False, A.device)
-        nsub = self.lib.scb_pass_nsub(path)
+        jp, nsub = self._plan(path, nA, nB, D, False, A.device)
         pm = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device)
         pl = torch.empty_like(pm)
         out = torch.empty(nA, dtype=torch.float32, device=A.device)
@@ -231,8 +233,7 @@ class CudaBackend:
         nA, D = A.shape
         nB = Ball.shape[0]
         path = self.path_for(A, Ball)
-        jp = self._jparts(path, nA, nB, D, True, A.device)
-        nsub = self.lib.scb_pass_nsub(path)
+        jp, nsub = self._plan(path, nA, nB, D, True, A.device)
         out = torch.empty(jp, nA, D, dtype=torch.float32, device=A.device)
         ws = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
         dA = torch.empty(nA, D, dtype=torch.float32, device=A.device)
@@ -255,8 +256,7 @@ class CudaBackend:
         nR, D = Xr.shape
         nAll = Xall.shape[0]
         path = self.path_for(Xr, Xall)
-        jp = self._jparts(path, nR, nAll, D, need_grad, Xr.device)
-        nsub = self.lib.scb_pass_nsub(path)
+        jp, nsub = self._plan(path, nR, nAll, D, need_grad, Xr.device)
         if sqn_all is None:
             sqn_all = self.row_sqnorm(Xall)
         if sqn_r is None:  # by contract Xr holds rows [row_offset, row_offset + nR) of Xall
@@ -296,8 +296,7 @@ class CudaBackend:
         nR, D = Xr.shape
         nAll = Xall.shape[0]
         path = self.path_for(Xr, Xall)
-        jp = self._jparts(path, nR, nAll, D, False, Xr.device)
-        nsub = self.lib.scb_pass_nsub(path)
+        jp, nsub = self._plan(path, nR, nAll, D, False, Xr.device)
         rs = torch.empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
         with torch.cuda.device(Xr.device):
             check(self.lib.scb_sparsify_sum_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),

@@ -15,6 +15,7 @@ int scb_tc_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64
                  int, float*, float*, float*, cudaStream_t);
 int scb_tc_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
 int scb_tc_set_flags(int);
+bool scb_tc_use_pair(int D, int grad);
 
 #define SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path)                                           \
   SCB_CHECK_ARG(scb_dtype_ok(dtype), SCB_E_DTYPE, "%s: unsupported dtype %d", __func__, (int)(dtype));             \
@@ -25,7 +26,43 @@ int scb_tc_set_flags(int);
   SCB_CHECK_ARG(((A) && (Bm)) || (nA) == 0, SCB_E_ARG, "%s: null operand", __func__);                              \
   SCB_CHECK_ARG((jparts) >= 1, SCB_E_ARG, "%s: jparts must be >= 1", __func__)
 
-extern "C" int scb_pass_nsub(int path) { return path == SCB_PATH_TC ? 2 : 1; }
+// Split the column sweep so that (row blocks x column groups x parts) fills the execution units evenly.
+// cost model: rounds of `n_units` concurrent work items x (tiles per item + 1 tile of prologue/drain).
+static int scb_choose_jparts(int64_t n_rb, int nsplit, int64_t n_jb, int n_units, int max_parts = 16) {
+  int best = 1;
+  double best_cost = -1.0;
+  const int hi = (int)(n_jb < max_parts ? n_jb : max_parts);
+  for (int jp = 1; jp <= (hi < 1 ? 1 : hi); ++jp) {
+    const int64_t rounds = (n_rb * nsplit * jp + n_units - 1) / n_units;
+    const double cost = (double)rounds * ((double)((n_jb + jp - 1) / jp) + 1.0);
+    if (best_cost < 0.0 || cost < best_cost - 1e-9) { best = jp; best_cost = cost; }
+  }
+  return best;
+}
+
+extern "C" int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, int n_sm, int* jparts, int* nsub) {
+  SCB_CHECK_ARG(path == SCB_PATH_SIMT || path == SCB_PATH_TC, SCB_E_ARG, "pass_plan: unknown path %d", path);
+  SCB_CHECK_ARG(nA >= 0 && nB >= 0 && D > 0 && n_sm > 0 && jparts && nsub, SCB_E_ARG, "pass_plan: bad argument");
+  if (path == SCB_PATH_TC) {
+    const int kch = (D + 63) / 64;
+    const int64_t n_rb = (nA + 127) / 128, n_jb = (nB + 127) / 128;
+    if (scb_tc_use_pair(D, grad) && n_sm >= 2) {       // one work item per CTA pair, no column groups
+      *jparts = scb_choose_jparts(n_rb, 1, n_jb, n_sm / 2);
+      *nsub = 4;
+    } else {
+      *jparts = scb_choose_jparts(n_rb, grad ? (kch + 3) / 4 : 1, n_jb, n_sm);
+      *nsub = 2;
+    }
+  } else {
+    const int64_t tiles = ((nA + 31) / 32) * (grad ? (D + 127) / 128 : 1);
+    int64_t jp = (2 * (int64_t)n_sm) / (tiles > 0 ? tiles : 1);
+    const int64_t cap = (nB + 31) / 32;
+    if (jp > cap) jp = cap;
+    *jparts = (int)(jp < 1 ? 1 : jp);
+    *nsub = 1;
+  }
+  return 0;
+}
 extern "C" int scb_set_tc_flags(int flags) { return scb_tc_set_flags(flags); }
 
 extern "C" int scb_lse_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,

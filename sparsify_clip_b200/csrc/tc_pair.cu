@@ -1,0 +1,567 @@
+// tc_pair.cu -- gradient passes on a CTA PAIR (thread-block cluster of 2, sm_100a) for 256 < D <= 512.
+//
+// Why a pair: the row-stationary output accumulator of a 128-row block is 128 x D fp32 = all 512 TMEM columns at
+// D = 512, which leaves no room for the S tile.  k_tc_pass therefore sweeps the columns once per 256-column output
+// group and recomputes S each time (3 contractions per sweep instead of 2).  Here the two CTAs of a cluster own
+// the SAME 128 rows and ONE HALF of the output columns each; the S tiles are computed once, alternately by the
+// two CTAs, and the 16-bit weight tile W = f(S) is handed to the peer through distributed shared memory:
+//
+//   tile t owned by CTA (t & 1):   MMA1  S = A_rb . Bm_t^T          (K = D, A stationary in smem)
+//                                  epi   W = f(S)  -> own TMEM (in place, TS-mode operand)
+//                                                  -> peer smem  (st.shared::cluster, 32 KB, K-major SW128)
+//   every tile, both CTAs:         MMA2  OUT[:, half] += W . Bm_t[:, half]   (own W from TMEM, peer's W from smem)
+//
+// Per pair and per two tiles the tensor pipes execute 2 x (2048 + 1024 + 1024) cycles = exactly the algorithmic
+// 2 contractions.  DSMEM traffic is 32 KB per CTA per two tiles (~8 B/clk of the measured ~20 B/clk).
+//
+// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue.
+// MMA issue order per CTA (lag 2, so that the epilogue of tile t hides behind three other MMAs):
+//   step t:  [MMA1(t) if own]  then  [MMA2(t-2)]
+// TMEM columns: OUT [0,256) | S0 [256,384) | S1 [384,512)   (W overwrites the first 32 columns of each 64-col half)
+// Shared memory: A kch x 16 KB | Wrecv 32 KB | ring nslots x 16 KB | column vector 1 KB | barriers
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+enum { M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2 };
+
+constexpr int kThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kSlotBytes = 128 * 64 * 2;   // one [128 x 64] 16-bit chunk
+constexpr int kMaxSlots = 8;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColOut = 0, kColS0 = 256;
+
+struct PairParams {
+  int64_t nA, nB;
+  int D, kch, n_rb, n_jb, jparts, nslots, fmt;
+  float p0;
+  const float* rowvec;
+  const float* colvec;
+  int64_t diag_off;
+  float* out;  // [jparts][nA][D]
+  float* s0;   // anchor: ws ; lunif: rq     [jparts*4][nA]
+  float* s1;   // lunif: rs
+};
+
+enum {
+  BAR_FULL = 0,                      // [kMaxSlots]
+  BAR_EMPTY = kMaxSlots,             // [kMaxSlots]
+  BAR_A_FULL = 2 * kMaxSlots,
+  BAR_A_EMPTY,
+  BAR_S_FULL,                        // [2]
+  BAR_S_EMPTY = BAR_S_FULL + 2,      // [2]
+  BAR_G_FULL = BAR_S_EMPTY + 2,      // [2]  own W tile stored in TMEM (8 epilogue warps)
+  BAR_OUT_FULL = BAR_G_FULL + 2,
+  BAR_OUT_EMPTY,
+  BAR_W_FULL,                        // peer's W tile landed in my Wrecv (8 remote arrivals)
+  BAR_W_EMPTY,                       // peer consumed the W tile I sent (peer's tcgen05.commit, multicast)
+  BAR_COUNT
+};
+
+struct Ring {
+  uint32_t slot, bits;
+  __device__ __forceinline__ uint32_t take(uint32_t n) {
+    const uint32_t s = slot;
+    slot = (slot + 1 == n) ? 0u : slot + 1;
+    return s;
+  }
+  __device__ __forceinline__ uint32_t parity_then_flip(uint32_t s) {
+    const uint32_t p = (bits >> s) & 1u;
+    bits ^= (1u << s);
+    return p;
+  }
+};
+
+// ---- cluster / DSMEM helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = ptx::globaltimer_ns();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (ptx::globaltimer_ns() - t0 > SCB_TC_WATCHDOG_NS) {
+      printf("scb200 watchdog (pair): block %d thread %d stuck on barrier tag %d parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, tag, parity);
+      __trap();
+    }
+  }
+}
+// arrive::one on the barrier at the same CTA-relative offset in every CTA of `mask`, once all tcgen05 operations
+// issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
+template <int MODE, int KCH>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PairParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs
+  const int kch = KCH ? KCH : P.kch;
+  const int kch_even = (kch + 1) & ~1;
+  const uint32_t sm_a = smem_base;
+  const uint32_t sm_w = sm_a + (uint32_t)kch * kSlotBytes;                  // Wrecv: 2 chunks
+  const uint32_t sm_ring = sm_w + 2u * kSlotBytes;
+  const uint32_t nslots = (uint32_t)P.nslots;
+  const uint32_t sm_cbuf = sm_ring + nslots * kSlotBytes;                   // 2 x 128 floats
+  const uint32_t sm_bar = sm_cbuf + 1024u;
+  const uint32_t sm_tmem_ptr = sm_bar + BAR_COUNT * 8u;
+  auto bar = [&](int i) -> uint32_t { return sm_bar + 8u * (uint32_t)i; };
+  uint8_t* gen_base = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  float* cbuf = reinterpret_cast<float*>(gen_base + (sm_cbuf - smem_base));
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sm_tmem_ptr - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();          // 0 / 1: which half of the output columns this CTA owns
+  const uint32_t peer = crank ^ 1u;
+  const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_items = P.n_rb * P.jparts;
+  const int gch = min(4, kch - 4 * (int)crank);      // 64-wide output chunks of my half
+  const int gch_even = (gch + 1) & ~1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kMaxSlots; ++i) { ptx::mbar_init(bar(BAR_FULL + i), 1); ptx::mbar_init(bar(BAR_EMPTY + i), 1); }
+    ptx::mbar_init(bar(BAR_A_FULL), 1);
+    ptx::mbar_init(bar(BAR_A_EMPTY), 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar(BAR_S_FULL + b), 1);
+      ptx::mbar_init(bar(BAR_S_EMPTY + b), 1);
+      ptx::mbar_init(bar(BAR_G_FULL + b), 8);
+    }
+    ptx::mbar_init(bar(BAR_OUT_FULL), 1);
+    ptx::mbar_init(bar(BAR_OUT_EMPTY), 8);
+    ptx::mbar_init(bar(BAR_W_FULL), 8);
+    ptx::mbar_init(bar(BAR_W_EMPTY), 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(sm_tmem_ptr, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the peer's barriers are initialised before anything remote touches them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_slot;
+
+  // item -> (row block, column part, tile range); `flip` alternates which CTA owns the even tiles
+#define SCB_PAIR_ITEM_SETUP()                                                                              \
+  const int rb = item % P.n_rb;                                                                            \
+  const int jp = item / P.n_rb;                                                                            \
+  const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts); \
+  const int nt = jb_hi - jb_lo;                                                                            \
+  const int t_first = (int)((crank ^ (item_cnt & 1u)) & 1u);  /* my own tiles: t_first, t_first + 2, ... */ \
+  const int n_own = (nt > t_first) ? (nt - t_first + 1) / 2 : 0;                                           \
+  (void)rb; (void)jp; (void)jb_lo; (void)n_own
+
+  // =========================================================================== TMA producer
+  if (warp == 0) {
+    Ring ring{0u, 0xFFFFFFFFu};
+    uint32_t a_empty_par = 1, item_cnt = 0;
+    for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
+      SCB_PAIR_ITEM_SETUP();
+      if (n_own > 0) {
+        ptx::mbar_wait(bar(BAR_A_EMPTY), a_empty_par, 100);
+        a_empty_par ^= 1;
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(bar(BAR_A_FULL), (uint32_t)kch * kSlotBytes);
+          for (int kc = 0; kc < kch; ++kc) ptx::tma_load_2d(sm_a + kc * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_A_FULL));
+        }
+        __syncwarp();
+      }
+      // one chunk slot; real == false burns the slot (keeps V pairs on even slots)
+      auto load_chunk = [&](bool real, int x, int y, int tag) {
+        const uint32_t s = ring.take(nslots);
+        ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), tag);
+        if (ptx::elect_one()) {
+          if (real) {
+            ptx::mbar_expect_tx(bar(BAR_FULL + s), (uint32_t)kSlotBytes);
+            ptx::tma_load_2d(sm_ring + s * kSlotBytes, &tmB, x, y, bar(BAR_FULL + s));
+          } else {
+            ptx::mbar_arrive(bar(BAR_FULL + s));
+          }
+        }
+        __syncwarp();
+      };
+      for (int t = 0; t < nt + 2; ++t) {
+        if (t < nt && ((t - t_first) & 1) == 0 && t >= t_first)
+          for (int kc = 0; kc < kch_even; ++kc) load_chunk(kc < kch, kc * 64, (jb_lo + t) * 128, 120);
+        if (t >= 2)
+          for (int c0 = 0; c0 < gch_even; ++c0) load_chunk(c0 < gch, (4 * (int)crank + c0) * 64, (jb_lo + t - 2) * 128, 121);
+      }
+    }
+  }
+  // =========================================================================== MMA issuer
+  else if (warp == 1) {
+    Ring ring{0u, 0u};
+    uint32_t a_full_par = 0, out_empty_par = 1, item_cnt = 0;
+    uint32_t k1 = 0, k2 = 0, kp = 0;   // issued MMA1 (own tiles), MMA2 on own tiles, MMA2 on peer tiles
+    const uint32_t idesc1 = ptx::idesc_f16(128, 128, P.fmt, P.fmt, 0, 0);
+    const uint32_t a_lo0 = ptx::desc_lo(sm_a, 16);
+    const uint32_t w_lo0 = ptx::desc_lo(sm_w, 16);
+    const uint32_t ring_lo0 = ptx::desc_lo(sm_ring, 16);
+    const uint32_t ring_v_lo0 = ptx::desc_lo(sm_ring, kSlotBytes);   // MN-major V: 64-wide blocks one chunk apart
+    constexpr uint32_t kChunkLo = kSlotBytes >> 4;
+    for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
+      SCB_PAIR_ITEM_SETUP();
+      if (n_own > 0) {
+        ptx::mbar_wait(bar(BAR_A_FULL), a_full_par, 200);
+        a_full_par ^= 1;
+      }
+      int own_left = n_own;
+      auto mma1 = [&]() {
+        const uint32_t b = k1 & 1u;
+        ptx::mbar_wait(bar(BAR_S_EMPTY + b), ((k1 >> 1) & 1u) ^ 1u, 210);
+        const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
+        auto kchunk = [&](int kc) {
+          const uint32_t s = ring.take(nslots);
+          ptx::mbar_wait(bar(BAR_FULL + s), ring.parity_then_flip(s), 212);
+          ptx::tc_fence_after();
+          const uint32_t alo = a_lo0 + (uint32_t)kc * kChunkLo, blo = ring_lo0 + s * kChunkLo;
+          if (ptx::elect_one()) {
+            if (kc < kch) {
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k)
+                ptx::umma_ss(d_tmem, ptx::desc_join(alo + 2u * k), ptx::desc_join(blo + 2u * k), idesc1,
+                             (uint32_t)((kc | (int)k) != 0));
+            }
+            ptx::umma_commit(bar(BAR_EMPTY + s));
+          }
+          __syncwarp();
+        };
+        if constexpr (KCH > 0) {
+#pragma unroll
+          for (int kc = 0; kc < KCH; ++kc) kchunk(kc);
+        } else {
+#pragma unroll 1
+          for (int kc = 0; kc < kch_even; ++kc) kchunk(kc);
+        }
+        --own_left;
+        if (ptx::elect_one()) {
+          ptx::umma_commit(bar(BAR_S_FULL + b));
+          if (own_left == 0) ptx::umma_commit(bar(BAR_A_EMPTY));
+        }
+        __syncwarp();
+        ++k1;
+      };
+      auto mma2 = [&](bool own, bool first, bool last) {
+        uint32_t b = 0;
+        if (own) {
+          b = k2 & 1u;
+          ptx::mbar_wait(bar(BAR_G_FULL + b), (k2 >> 1) & 1u, 220);
+        } else {
+          mbar_wait_cluster(bar(BAR_W_FULL), kp & 1u, 225);
+          fence_proxy_async_all();
+        }
+        if (first) {
+          ptx::mbar_wait(bar(BAR_OUT_EMPTY), out_empty_par, 221);
+          out_empty_par ^= 1;
+        }
+        const uint32_t g_tmem = tmem_base + kColS0 + 128u * b;
+#pragma unroll
+        for (int c0 = 0; c0 < 4; c0 += 2) {      // output columns [64 c0, 64 c0 + 64 n) of my half
+          if (c0 >= gch_even) break;
+          const int n = min(2, gch - c0);
+          const uint32_t sv = ring.take(nslots);
+          ptx::mbar_wait(bar(BAR_FULL + sv), ring.parity_then_flip(sv), 222);
+          const uint32_t sv1 = ring.take(nslots);
+          ptx::mbar_wait(bar(BAR_FULL + sv1), ring.parity_then_flip(sv1), 223);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + kColOut + 64u * (uint32_t)c0;
+          const uint32_t idesc2 = ptx::idesc_f16(128, 64 * n, P.fmt, P.fmt, 0, 1);
+          const uint32_t vlo = ring_v_lo0 + sv * kChunkLo;
+          const bool last_group = (c0 + 2 >= gch_even);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < 8; ++ks) {
+              const uint64_t bdesc = ptx::desc_join(vlo + 128u * ks);
+              const uint32_t accum = (uint32_t)!(first && ks == 0);
+              if (own)
+                ptx::umma_ts(d_tmem, g_tmem + (ks >> 2) * 64u + (ks & 3u) * 8u, bdesc, idesc2, accum);
+              else
+                ptx::umma_ss(d_tmem, ptx::desc_join(w_lo0 + (ks >> 2) * kChunkLo + (ks & 3u) * 2u), bdesc, idesc2, accum);
+            }
+            ptx::umma_commit(bar(BAR_EMPTY + sv));
+            ptx::umma_commit(bar(BAR_EMPTY + sv1));
+            if (last_group) {
+              if (own) ptx::umma_commit(bar(BAR_S_EMPTY + b));
+              else umma_commit_mc(bar(BAR_W_EMPTY), (uint16_t)(1u << peer));
+              if (last) ptx::umma_commit(bar(BAR_OUT_FULL));
+            }
+          }
+          __syncwarp();
+        }
+        if (own) ++k2; else ++kp;
+      };
+      for (int t = 0; t < nt + 2; ++t) {
+        if (t < nt && t >= t_first && ((t - t_first) & 1) == 0) mma1();
+        if (t >= 2) {
+          const int tt = t - 2;
+          mma2(tt >= t_first && ((tt - t_first) & 1) == 0, tt == 0, tt == nt - 1);
+        }
+      }
+    }
+  }
+  // =========================================================================== epilogue warps
+  else if (warp >= 4) {
+    const int e = warp - 4;
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int h = e >> 2;         // which 64-column half of the S tile
+    const int rrow = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const uint32_t peer_w = mapa(sm_w, peer);
+    const uint32_t peer_w_full = mapa(bar(BAR_W_FULL), peer);
+    uint32_t ke = 0, item_cnt = 0;
+    for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
+      SCB_PAIR_ITEM_SETUP();
+      const int64_t gi = (int64_t)rb * 128 + rrow;
+      const bool row_ok = gi < P.nA;
+      float rowc = 0.f;
+      if (MODE == M_ANCHOR_GRAD) rowc = row_ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
+      if (MODE == M_LUNIF_GRAD) rowc = row_ok ? P.rowvec[gi] * P.p0 : 0.f;
+      float st0 = 0.f, st1 = 0.f;
+      const int64_t my_diag_col = gi + P.diag_off;
+
+      for (int t = t_first; t < nt; t += 2, ++ke) {
+        const uint32_t b = ke & 1u;
+        const int jb = jb_lo + t;
+        const int64_t col0 = (int64_t)jb * 128 + 64 * h;
+        const bool tile_partial = ((int64_t)jb * 128 + 128) > P.nB;
+        {
+          const int idx = e * 32 + lane;
+          if (idx < 128) {
+            const int64_t gj = (int64_t)jb * 128 + idx;
+            float cv = INFINITY;
+            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * P.p0;
+            cbuf[b * 128 + idx] = cv;
+          }
+          ptx::named_bar_sync(1, kEpiThreads);
+        }
+        ptx::mbar_wait(bar(BAR_S_FULL + b), (ke >> 1) & 1u, 300);
+        ptx::tc_fence_after();
+        const int64_t drow0 = (int64_t)rb * 128 + 32 * q + P.diag_off;
+        const bool diag_here = (drow0 < col0 + 64) && (drow0 + 32 > col0);
+
+        uint32_t packed[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b + 64u * h + 32u * cc, v);
+          ptx::tmem_ld_wait();
+          const int64_t cbase = col0 + 32 * cc;
+          const float* cb = cbuf + b * 128 + 64 * h + 32 * cc;
+          const int dcol = diag_here ? (int)(my_diag_col - cbase) : -1;
+          if (tile_partial && MODE == M_ANCHOR_GRAD) {
+            const int nvalid = (int)min((int64_t)32, max((int64_t)0, P.nB - cbase));
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c >= nvalid) v[c] = __float_as_uint(-1e30f);
+          }
+          float w[32];
+          if (MODE == M_ANCHOR_GRAD) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float g = __uint_as_float(v[c]);
+              const float y = g * P.p0;
+              const float ww = scb_ex2(y - rowc) + scb_ex2(y - cb[c]);   // dead columns: 0 + 0
+              st0 = fmaf(ww, g, st0);
+              w[c] = ww;
+            }
+          } else {  // lunif: exp2(2 p0 g - p0 n_i - p0 n_j); dead columns carry +inf in cb -> 0
+            const float two_p0 = 2.f * P.p0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) w[c] = scb_ex2(fmaf(__uint_as_float(v[c]), two_p0, -(rowc + cb[c])));
+          }
+          if (diag_here) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c == dcol) w[c] = 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const uint32_t pk = P.fmt ? ptx::pack_bf16(w[2 * c], w[2 * c + 1]) : ptx::pack_f16(w[2 * c], w[2 * c + 1]);
+            packed[16 * cc + c] = pk;
+            if (MODE == M_LUNIF_GRAD) {
+              st1 += w[2 * c] + w[2 * c + 1];
+              if (P.fmt) {
+                st0 += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
+              } else {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                st0 += f.x + f.y;
+              }
+            }
+          }
+        }
+        // ---- own copy: weights overwrite the first 32 columns of this warp's half of the S buffer (TS-mode MMA2)
+        ptx::tmem_st32(tmem_base + lane_addr + kColS0 + 128u * b + 64u * h, packed);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(BAR_G_FULL + b));
+        // ---- peer copy: K-major SW128 image in the peer's Wrecv (once the peer has consumed the previous one)
+        ptx::mbar_wait(bar(BAR_W_EMPTY), (ke & 1u) ^ 1u, 310);
+        {
+          const uint32_t row_addr = peer_w + (uint32_t)h * kSlotBytes + (uint32_t)rrow * 128u;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            st_cluster_v4(row_addr + (uint32_t)((u ^ (rrow & 7)) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
+                          packed[4 * u + 3]);
+          fence_proxy_async_all();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(peer_w_full);
+        }
+      }  // own tiles
+
+      // ---- drain my half of the output accumulator
+      if (nt > 0) {
+        ptx::mbar_wait(bar(BAR_OUT_FULL), item_cnt & 1u, 320);
+        ptx::tc_fence_after();
+        const int ncol_half = 32 * gch;  // columns of OUT handled by this warp
+        float* orow = P.out + ((int64_t)jp * P.nA + gi) * P.D;
+        for (int c0 = 0; c0 < ncol_half; c0 += 32) {
+          uint32_t v[32];
+          const int ocol = h * ncol_half + c0;
+          ptx::tmem_ld32(tmem_base + lane_addr + kColOut + (uint32_t)ocol, v);
+          ptx::tmem_ld_wait();
+          const int d0 = 256 * (int)crank + ocol;
+          if (row_ok) {
+            if (d0 + 32 <= P.D) {
+#pragma unroll
+              for (int c = 0; c < 32; c += 4)
+                *reinterpret_cast<float4*>(orow + d0 + c) = make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]),
+                                                                        __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (d0 + c < P.D) orow[d0 + c] = __uint_as_float(v[c]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(BAR_OUT_EMPTY));
+      }
+      if (row_ok) {   // statistics over MY tiles only: 4 sub-partials per part (CTA rank x column half)
+        const int64_t o = ((int64_t)jp * 4 + 2 * (int)crank + h) * P.nA + gi;
+        if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
+        if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
+      }
+    }  // items
+  }
+#undef SCB_PAIR_ITEM_SETUP
+
+  // =========================================================================== teardown
+  // nobody leaves while the peer may still write into this CTA's shared memory or signal its barriers
+  ptx::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int scb_make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype);   // tc_pass.cu
+
+namespace {
+
+template <int MODE>
+int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                PairParams P, cudaStream_t s) {
+  if (nA == 0) return 0;
+  P.nA = nA; P.nB = nB; P.D = D;
+  P.kch = (D + 63) / 64;
+  P.n_rb = (int)((nA + 127) / 128);
+  P.n_jb = (int)((nB + 127) / 128);
+  SCB_CHECK_ARG(P.kch > 4 && P.kch <= 8, SCB_E_SHAPE, "pair kernel needs 256 < D <= 512 (D=%d)", D);
+  SCB_CHECK_ARG(P.jparts >= 1 && P.jparts <= P.n_jb, SCB_E_ARG, "jparts=%d outside [1, %d]", P.jparts, P.n_jb);
+  P.fmt = (dtype == SCB_BF16) ? 1 : 0;
+  const int budget = 232448 - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
+  int nslots = (budget - (P.kch + 2) * kSlotBytes) / kSlotBytes;
+  nslots &= ~1;
+  if (nslots > kMaxSlots) nslots = kMaxSlots;
+  SCB_CHECK_ARG(nslots >= 4, SCB_E_SHAPE, "not enough shared memory for the chunk ring (D=%d)", D);
+  P.nslots = nslots;
+  const size_t smem = (size_t)(P.kch + 2 + nslots) * kSlotBytes + 3 * 1024;
+
+  CUtensorMap tmA, tmB;
+  int rc = scb_make_tmap_2d(&tmA, A, nA, D, ldA, dtype);
+  if (rc) return rc;
+  rc = scb_make_tmap_2d(&tmB, Bm, nB, D, ldB, dtype);
+  if (rc) return rc;
+
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_pair<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_pair<MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) { scb_set_error("cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  const int n_items = P.n_rb * P.jparts;
+  const int max_pairs = num_sms / 2;
+  const int n_pairs = n_items < max_pairs ? n_items : max_pairs;
+  if (P.kch == 8) k_tc_pair<MODE, 8><<<2 * n_pairs, kThreads, smem, s>>>(tmA, tmB, P);
+  else k_tc_pair<MODE, 0><<<2 * n_pairs, kThreads, smem, s>>>(tmA, tmB, P);
+  SCB_CHECK_LAUNCH("tc_pair");
+  return 0;
+}
+
+}  // namespace
+
+int scb_tc_pair_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                            float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts,
+                            float* out, float* ws, cudaStream_t s) {
+  PairParams P{};
+  P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.rowvec = row_lse; P.colvec = col_lse; P.diag_off = diag_off;
+  P.out = out; P.s0 = ws;
+  return launch_pair<M_ANCHOR_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
+}
+int scb_tc_pair_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll, int dtype,
+                      float t, const float* sqn_r, const float* sqn_all, int64_t row_offset, int jparts, float* U,
+                      float* rq, float* rs, cudaStream_t s) {
+  PairParams P{};
+  P.jparts = jparts; P.p0 = t * SCB_LOG2E; P.rowvec = sqn_r; P.colvec = sqn_all; P.diag_off = row_offset;
+  P.out = U; P.s0 = rq; P.s1 = rs;
+  return launch_pair<M_LUNIF_GRAD>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
+}

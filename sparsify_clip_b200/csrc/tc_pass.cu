@@ -535,6 +535,7 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld,
 }
 
 int g_tc_flags = 1;   // bit0: weight tile in TMEM (TS-mode MMA2) -- measured faster than the smem variant
+                      // bit1: CTA-pair kernel (tc_pair.cu) for the gradient passes when 256 < D <= 512
 
 template <int MODE>
 int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
@@ -592,6 +593,18 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
 }  // namespace
 
 int scb_tc_set_flags(int flags) { int o = g_tc_flags; g_tc_flags = flags; return o; }
+int scb_make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype) {
+  return make_tmap(m, base, rows, D, ld, dtype);
+}
+// the gradient passes run on a CTA pair (one S tile per two output halves) when the output needs two column groups
+bool scb_tc_use_pair(int D, int grad) {
+  const int kch = (D + 63) / 64;
+  return grad && (g_tc_flags & 2) && kch > 4 && kch <= 8;
+}
+int scb_tc_pair_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*,
+                            const float*, int64_t, int, float*, float*, cudaStream_t);
+int scb_tc_pair_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
+                      int64_t, int, float*, float*, float*, cudaStream_t);
 
 int scb_tc_lse(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype, float scale,
                int jparts, float* pm, float* pl, cudaStream_t s) {
@@ -602,6 +615,9 @@ int scb_tc_lse(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int
 int scb_tc_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                        float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts, float* out,
                        float* ws, cudaStream_t s) {
+  if (scb_tc_use_pair(D, 1) && (dtype == SCB_BF16 || dtype == SCB_F16) && D % 8 == 0 && ldA % 8 == 0 && ldB % 8 == 0 &&
+      scb_aligned16(A) && scb_aligned16(Bm))
+    return scb_tc_pair_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s);
   TcParams P{};
   P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.rowvec = row_lse; P.colvec = col_lse; P.diag_off = diag_off;
   P.out = out; P.s0 = ws;
@@ -610,6 +626,9 @@ int scb_tc_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, in
 int scb_tc_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll, int dtype,
                  float t, const float* sqn_r, const float* sqn_all, int64_t row_offset, int jparts, float* U, float* rq,
                  float* rs, cudaStream_t s) {
+  if (U && scb_tc_use_pair(D, 1) && (dtype == SCB_BF16 || dtype == SCB_F16) && D % 8 == 0 && ldR % 8 == 0 &&
+      ldAll % 8 == 0 && scb_aligned16(Xr) && scb_aligned16(Xall))
+    return scb_tc_pair_lunif(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, t, sqn_r, sqn_all, row_offset, jparts, U, rq, rs, s);
   TcParams P{};
   P.jparts = jparts; P.p0 = t * SCB_LOG2E; P.rowvec = sqn_r; P.colvec = sqn_all; P.diag_off = row_offset;
   P.out = U; P.s0 = rq; P.s1 = rs;

@@ -39,7 +39,26 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/scb200.h but not exported"
     assert set(_lib.SIGNATURES) | {"scb_last_error"} == set(declared)
     assert _lib.load().scb_version() >= 100
-    assert _lib.load().scb_pass_nsub(_lib.PATH_TC) == 2 and _lib.load().scb_pass_nsub(_lib.PATH_SIMT) == 1
+
+
+def _plan(path, nA, nB, D, grad, n_sm=148):
+    jp, nsub = ctypes.c_int(0), ctypes.c_int(0)
+    assert _lib.load().scb_pass_plan(path, nA, nB, D, grad, n_sm, ctypes.byref(jp), ctypes.byref(nsub)) == 0
+    return jp.value, nsub.value
+
+
+def test_pass_plan_matches_the_host_mirror():
+    """scb_pass_plan (the planner the backend uses) against choose_jparts, plus the nsub contract."""
+    assert _plan(_lib.PATH_SIMT, 1000, 1000, 512, 1)[1] == 1
+    for nA, nB, D in [(32768, 32768, 512), (4096, 4096, 512), (1000, 1000, 768), (4096, 32768, 512), (130, 130, 72),
+                      (65536 // 8, 65536, 768), (128, 128, 256)]:
+        n_rb, n_jb, kch = (nA + 127) // 128, (nB + 127) // 128, (D + 63) // 64
+        assert _plan(_lib.PATH_TC, nA, nB, D, 0) == (scb.choose_jparts(n_rb, 1, n_jb, 148), 2)
+        jp, nsub = _plan(_lib.PATH_TC, nA, nB, D, 1)
+        if 4 < kch <= 8:      # gradient passes on CTA pairs: 74 pair-units, one item per row block and part
+            assert (jp, nsub) == (scb.choose_jparts(n_rb, 1, n_jb, 74), 4)
+        else:
+            assert (jp, nsub) == (scb.choose_jparts(n_rb, (kch + 3) // 4, n_jb, 148), 2)
 
 
 def test_argument_errors_are_reported_without_a_gpu():
