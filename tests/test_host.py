@@ -50,12 +50,21 @@ def _plan(path, nA, nB, D, grad, n_sm=148):
 def test_pass_plan_matches_the_host_mirror():
     """scb_pass_plan (the planner the backend uses) against choose_jparts, plus the nsub contract."""
     assert _plan(_lib.PATH_SIMT, 1000, 1000, 512, 1)[1] == 1
+    for flags in (1, 3):
+        prev = _lib.load().scb_set_tc_flags(flags)
+        try:
+            _check_tc_plans(pair=bool(flags & 2))
+        finally:
+            _lib.load().scb_set_tc_flags(prev)
+
+
+def _check_tc_plans(pair):
     for nA, nB, D in [(32768, 32768, 512), (4096, 4096, 512), (1000, 1000, 768), (4096, 32768, 512), (130, 130, 72),
                       (65536 // 8, 65536, 768), (128, 128, 256)]:
         n_rb, n_jb, kch = (nA + 127) // 128, (nB + 127) // 128, (D + 63) // 64
         assert _plan(_lib.PATH_TC, nA, nB, D, 0) == (scb.choose_jparts(n_rb, 1, n_jb, 148), 2)
         jp, nsub = _plan(_lib.PATH_TC, nA, nB, D, 1)
-        if 4 < kch <= 8:      # gradient passes on CTA pairs: 74 pair-units, one item per row block and part
+        if pair and 4 < kch <= 8:      # gradient passes on CTA pairs: 74 pair-units, one item per row block and part
             assert (jp, nsub) == (scb.choose_jparts(n_rb, 1, n_jb, 74), 4)
         else:
             assert (jp, nsub) == (scb.choose_jparts(n_rb, (kch + 3) // 4, n_jb, 148), 2)
