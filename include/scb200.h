@@ -148,6 +148,10 @@ int scb_lunif_grad_finalize(const float* U, int jparts, const float* rq, int npa
 int scb_sparsify_sum_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
                           int dtype, int64_t row_offset, int jparts, float* rs, int path, void* stream);
 
+/* debug: device buffer of 2 x 4 x 4096 x 2 uint64 that the CTA-pair kernel fills with a per-role timeline of
+ * cluster 0 (tag, tile, clock64) on the following launches; NULL switches it off (tools/pair_trace.py). */
+int scb_debug_pair_trace(void* buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,7 @@ SIGNATURES = {
     "scb_lunif_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp],
     "scb_lunif_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _i32, _vp],
     "scb_lunif_grad_finalize": [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _i64, _i32, _f32, _vp, _i32, _vp, _vp],
+    "scb_debug_pair_trace": [_vp],
     "scb_sparsify_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _i64, _i32, _vp, _i32, _vp],
 }
 
@@ -73,6 +74,8 @@ def load(build_if_missing=True):
         fn.restype = ctypes.c_int
     lib.scb_last_error.argtypes = []
     lib.scb_last_error.restype = ctypes.c_char_p
+    if os.environ.get("SCB_TC_FLAGS"):          # tuning/debug knob, see scb_set_tc_flags in include/scb200.h
+        lib.scb_set_tc_flags(int(os.environ["SCB_TC_FLAGS"]))
     _lib = lib
     return lib
 

@@ -14,7 +14,10 @@
 // Per pair and per two tiles the tensor pipes execute 2 x (2048 + 1024 + 1024) cycles = exactly the algorithmic
 // 2 contractions.  DSMEM traffic is 32 KB per CTA per two tiles (~8 B/clk of the measured ~20 B/clk).
 //
-// Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue.
+// Roles (512 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue,
+// warps 12-15 W senders (read the finished weight tile back from TMEM and push it to the peer with st.async, so that
+// the DSMEM store back-pressure -- ~3000 cycles per 32 KB tile, measured -- never blocks the epilogue warps).
+// Registers are rebalanced with setmaxnreg: 80 (control) / 168 (epilogue) / 96 (senders) = 64 K.
 // MMA issue order per CTA (lag 2, so that the epilogue of tile t hides behind three other MMAs):
 //   step t:  [MMA1(t) if own]  then  [MMA2(t-2)]
 // TMEM columns: OUT [0,256) | S0 [256,384) | S1 [384,512)   (W overwrites the first 32 columns of each 64-col half)
@@ -26,10 +29,14 @@ namespace {
 
 enum { M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2 };
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 constexpr int kEpiThreads = 256;
 constexpr int kSlotBytes = 128 * 64 * 2;   // one [128 x 64] 16-bit chunk
 constexpr int kMaxSlots = 8;
+constexpr int kAStat = 6;                  // K-chunks of A resident in smem; the rest stream with the column tile
+                                           // (frees ring slots: the ring, not the tensor pipe, was the bottleneck)
+constexpr int kPeerLag = 3;                // MMA2 of a peer tile is issued this many steps after the tile (odd:
+                                           // it lands on my own steps); hides epilogue + DSMEM latency of the peer
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColOut = 0, kColS0 = 256;
 
@@ -43,6 +50,26 @@ struct PairParams {
   float* out;  // [jparts][nA][D]
   float* s0;   // anchor: ws ; lunif: rq     [jparts*4][nA]
   float* s1;   // lunif: rs
+  unsigned long long* trace;   // debug timeline (scb_debug_pair_trace), normally null
+  int dbg;                     // timing experiments only (bit0: skip the W transfer -> WRONG results)
+};
+
+// Debug timeline: cluster 0 records (tag, tile, clock64) per role; kTraceCap events per (CTA rank, role).
+constexpr int kTraceCap = 4096;
+struct Tracer {
+  unsigned long long* base;
+  uint32_t n;
+  __device__ __forceinline__ void init(unsigned long long* trace, int pair_id, uint32_t crank, int role) {
+    base = (trace && pair_id == 0) ? trace + ((size_t)(crank * 4 + role) * kTraceCap) * 2 : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void rec(uint32_t tag, uint32_t tile) {
+    if (base && n < kTraceCap) {
+      base[2 * n] = ((unsigned long long)tag << 32) | tile;
+      base[2 * n + 1] = (unsigned long long)clock64();
+      ++n;
+    }
+  }
 };
 
 enum {
@@ -55,7 +82,7 @@ enum {
   BAR_G_FULL = BAR_S_EMPTY + 2,      // [2]  own W tile stored in TMEM (8 epilogue warps)
   BAR_OUT_FULL = BAR_G_FULL + 2,
   BAR_OUT_EMPTY,
-  BAR_W_FULL,                        // peer's W tile landed in my Wrecv (8 remote arrivals)
+  BAR_W_FULL,                        // peer's W tile landed in my Wrecv (32 KB of st.async complete_tx)
   BAR_W_EMPTY,                       // peer consumed the W tile I sent (peer's tcgen05.commit, multicast)
   BAR_COUNT
 };
@@ -88,13 +115,16 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// 16-byte asynchronous store into the peer's shared memory; completes 16 tx-bytes on the peer's mbarrier when the
+// data has landed, so the sender needs no fence and no arrive (a release.cluster arrive behind generic
+// st.shared::cluster stores costs MEMBAR.ALL.GPU + ERRBAR per warp: measured 50% of the epilogue time).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -130,9 +160,10 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs
   const int kch = KCH ? KCH : P.kch;
-  const int kch_even = (kch + 1) & ~1;
+  const int n_astat = KCH ? (KCH < kAStat ? KCH : kAStat) : min(kch, kAStat);
+  const int b1_slots = 2 * kch - n_astat;                                   // ring slots one S tile consumes
   const uint32_t sm_a = smem_base;
-  const uint32_t sm_w = sm_a + (uint32_t)kch * kSlotBytes;                  // Wrecv: 2 chunks
+  const uint32_t sm_w = sm_a + (uint32_t)n_astat * kSlotBytes;              // Wrecv: 2 chunks
   const uint32_t sm_ring = sm_w + 2u * kSlotBytes;
   const uint32_t nslots = (uint32_t)P.nslots;
   const uint32_t sm_cbuf = sm_ring + nslots * kSlotBytes;                   // 2 x 128 floats
@@ -161,12 +192,12 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     ptx::mbar_init(bar(BAR_A_EMPTY), 1);
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(bar(BAR_S_FULL + b), 1);
-      ptx::mbar_init(bar(BAR_S_EMPTY + b), 1);
+      ptx::mbar_init(bar(BAR_S_EMPTY + b), 5);   // MMA2 commit + the 4 sender warps (W read back from TMEM)
       ptx::mbar_init(bar(BAR_G_FULL + b), 8);
     }
     ptx::mbar_init(bar(BAR_OUT_FULL), 1);
     ptx::mbar_init(bar(BAR_OUT_EMPTY), 8);
-    ptx::mbar_init(bar(BAR_W_FULL), 8);
+    ptx::mbar_init(bar(BAR_W_FULL), 1);      // armed by my MMA warp with expect_tx(32 KB); bytes come from the peer
     ptx::mbar_init(bar(BAR_W_EMPTY), 1);
     ptx::fence_barrier_init();
   }
@@ -187,8 +218,13 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int n_own = (nt > t_first) ? (nt - t_first + 1) / 2 : 0;                                           \
   (void)rb; (void)jp; (void)jb_lo; (void)n_own
 
+  // (setmaxnreg sits at the top of each role branch so that the role's code is dominated by it: ptxas only
+  //  budgets registers per region when that holds)
   // =========================================================================== TMA producer
   if (warp == 0) {
+    setmaxnreg_dec<80>();
+    Tracer tr; tr.init(P.trace, pair_id, crank, 0);
+    if (lane == 0) { tr.rec(0, (uint32_t)(ptx::globaltimer_ns() & 0xffffffffu)); tr.rec(0, (uint32_t)(ptx::globaltimer_ns() >> 32)); }
     Ring ring{0u, 0xFFFFFFFFu};
     uint32_t a_empty_par = 1, item_cnt = 0;
     for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
@@ -197,35 +233,47 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ptx::mbar_wait(bar(BAR_A_EMPTY), a_empty_par, 100);
         a_empty_par ^= 1;
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(bar(BAR_A_FULL), (uint32_t)kch * kSlotBytes);
-          for (int kc = 0; kc < kch; ++kc) ptx::tma_load_2d(sm_a + kc * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_A_FULL));
+          ptx::mbar_expect_tx(bar(BAR_A_FULL), (uint32_t)n_astat * kSlotBytes);
+          for (int kc = 0; kc < n_astat; ++kc) ptx::tma_load_2d(sm_a + kc * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_A_FULL));
         }
         __syncwarp();
       }
       // one chunk slot; real == false burns the slot (keeps V pairs on even slots)
-      auto load_chunk = [&](bool real, int x, int y, int tag) {
+      auto load_chunk = [&](bool real, const CUtensorMap* tm, int x, int y, int tag) {
         const uint32_t s = ring.take(nslots);
         ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), tag);
+        if (lane == 0) tr.rec((uint32_t)tag, (uint32_t)y);
         if (ptx::elect_one()) {
           if (real) {
             ptx::mbar_expect_tx(bar(BAR_FULL + s), (uint32_t)kSlotBytes);
-            ptx::tma_load_2d(sm_ring + s * kSlotBytes, &tmB, x, y, bar(BAR_FULL + s));
+            ptx::tma_load_2d(sm_ring + s * kSlotBytes, tm, x, y, bar(BAR_FULL + s));
           } else {
             ptx::mbar_arrive(bar(BAR_FULL + s));
           }
         }
         __syncwarp();
       };
-      for (int t = 0; t < nt + 2; ++t) {
-        if (t < nt && ((t - t_first) & 1) == 0 && t >= t_first)
-          for (int kc = 0; kc < kch_even; ++kc) load_chunk(kc < kch, kc * 64, (jb_lo + t) * 128, 120);
-        if (t >= 2)
-          for (int c0 = 0; c0 < gch_even; ++c0) load_chunk(c0 < gch, (4 * (int)crank + c0) * 64, (jb_lo + t - 2) * 128, 121);
+      auto load_v = [&](int tt, int tag) {
+        for (int c0 = 0; c0 < gch_even; ++c0) load_chunk(c0 < gch, &tmB, (4 * (int)crank + c0) * 64, (jb_lo + tt) * 128, tag);
+      };
+      // my steps are the steps of my own tiles: [MMA1(t)] [MMA2 own (t-2)] [MMA2 peer (t-kPeerLag)]
+      for (int t = t_first; t < nt + kPeerLag + 1; t += 2) {
+        if (t < nt) {
+          for (int kc = 0; kc < kch; ++kc) {
+            if (kc >= n_astat) load_chunk(true, &tmA, kc * 64, rb * 128, 119);
+            load_chunk(true, &tmB, kc * 64, (jb_lo + t) * 128, 120);
+          }
+          if (b1_slots & 1) load_chunk(false, &tmB, 0, 0, 118);
+        }
+        if (t - 2 >= 0 && t - 2 < nt) load_v(t - 2, 121);
+        if (t - kPeerLag >= 0 && t - kPeerLag < nt) load_v(t - kPeerLag, 122);
       }
     }
   }
   // =========================================================================== MMA issuer
   else if (warp == 1) {
+    setmaxnreg_dec<80>();
+    Tracer tr; tr.init(P.trace, pair_id, crank, 1);
     Ring ring{0u, 0u};
     uint32_t a_full_par = 0, out_empty_par = 1, item_cnt = 0;
     uint32_t k1 = 0, k2 = 0, kp = 0;   // issued MMA1 (own tiles), MMA2 on own tiles, MMA2 on peer tiles
@@ -244,20 +292,31 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int own_left = n_own;
       auto mma1 = [&]() {
         const uint32_t b = k1 & 1u;
+        if (lane == 0) tr.rec(10, k1);
         ptx::mbar_wait(bar(BAR_S_EMPTY + b), ((k1 >> 1) & 1u) ^ 1u, 210);
+        if (lane == 0) tr.rec(11, k1);
         const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
         auto kchunk = [&](int kc) {
+          uint32_t alo, sa = 0;
+          const bool a_streamed = kc >= n_astat;
+          if (a_streamed) {
+            sa = ring.take(nslots);
+            ptx::mbar_wait(bar(BAR_FULL + sa), ring.parity_then_flip(sa), 211);
+            alo = ring_lo0 + sa * kChunkLo;
+          } else {
+            alo = a_lo0 + (uint32_t)kc * kChunkLo;
+          }
           const uint32_t s = ring.take(nslots);
           ptx::mbar_wait(bar(BAR_FULL + s), ring.parity_then_flip(s), 212);
+          if (lane == 0) tr.rec(12, (uint32_t)kc);
           ptx::tc_fence_after();
-          const uint32_t alo = a_lo0 + (uint32_t)kc * kChunkLo, blo = ring_lo0 + s * kChunkLo;
+          const uint32_t blo = ring_lo0 + s * kChunkLo;
           if (ptx::elect_one()) {
-            if (kc < kch) {
 #pragma unroll
-              for (uint32_t k = 0; k < 4; ++k)
-                ptx::umma_ss(d_tmem, ptx::desc_join(alo + 2u * k), ptx::desc_join(blo + 2u * k), idesc1,
-                             (uint32_t)((kc | (int)k) != 0));
-            }
+            for (uint32_t k = 0; k < 4; ++k)
+              ptx::umma_ss(d_tmem, ptx::desc_join(alo + 2u * k), ptx::desc_join(blo + 2u * k), idesc1,
+                           (uint32_t)((kc | (int)k) != 0));
+            if (a_streamed) ptx::umma_commit(bar(BAR_EMPTY + sa));
             ptx::umma_commit(bar(BAR_EMPTY + s));
           }
           __syncwarp();
@@ -267,7 +326,13 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int kc = 0; kc < KCH; ++kc) kchunk(kc);
         } else {
 #pragma unroll 1
-          for (int kc = 0; kc < kch_even; ++kc) kchunk(kc);
+          for (int kc = 0; kc < kch; ++kc) kchunk(kc);
+        }
+        if (b1_slots & 1) {     // padding slot (keeps the V pairs on even slots)
+          const uint32_t s = ring.take(nslots);
+          ptx::mbar_wait(bar(BAR_FULL + s), ring.parity_then_flip(s), 213);
+          if (ptx::elect_one()) ptx::umma_commit(bar(BAR_EMPTY + s));
+          __syncwarp();
         }
         --own_left;
         if (ptx::elect_one()) {
@@ -279,13 +344,17 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       };
       auto mma2 = [&](bool own, bool first, bool last) {
         uint32_t b = 0;
+        if (lane == 0) tr.rec(own ? 20 : 30, own ? k2 : kp);
         if (own) {
           b = k2 & 1u;
           ptx::mbar_wait(bar(BAR_G_FULL + b), (k2 >> 1) & 1u, 220);
         } else {
-          mbar_wait_cluster(bar(BAR_W_FULL), kp & 1u, 225);
-          fence_proxy_async_all();
+          if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL), (P.dbg & 1) ? 2048u : 2u * kSlotBytes);
+          __syncwarp();
+          ptx::mbar_wait(bar(BAR_W_FULL), kp & 1u, 225);
+          ptx::fence_proxy_async_smem();
         }
+        if (lane == 0) tr.rec(own ? 21 : 31, own ? k2 : kp);
         if (first) {
           ptx::mbar_wait(bar(BAR_OUT_EMPTY), out_empty_par, 221);
           out_empty_par ^= 1;
@@ -299,6 +368,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           ptx::mbar_wait(bar(BAR_FULL + sv), ring.parity_then_flip(sv), 222);
           const uint32_t sv1 = ring.take(nslots);
           ptx::mbar_wait(bar(BAR_FULL + sv1), ring.parity_then_flip(sv1), 223);
+          if (lane == 0) tr.rec(own ? 22 : 32, (uint32_t)c0);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + kColOut + 64u * (uint32_t)c0;
           const uint32_t idesc2 = ptx::idesc_f16(128, 64 * n, P.fmt, P.fmt, 0, 1);
@@ -323,28 +393,31 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
           }
           __syncwarp();
+          if (lane == 0) tr.rec(own ? 23 : 33, (uint32_t)c0);
         }
         if (own) ++k2; else ++kp;
       };
-      for (int t = 0; t < nt + 2; ++t) {
-        if (t < nt && t >= t_first && ((t - t_first) & 1) == 0) mma1();
-        if (t >= 2) {
-          const int tt = t - 2;
-          mma2(tt >= t_first && ((tt - t_first) & 1) == 0, tt == 0, tt == nt - 1);
-        }
+      int m2_left = nt;          // the first MMA2 of the item overwrites OUT, the last one publishes it
+      for (int t = t_first; t < nt + kPeerLag + 1; t += 2) {
+        if (t < nt) mma1();
+        if (t - 2 >= 0 && t - 2 < nt) { mma2(true, m2_left == nt, m2_left == 1); --m2_left; }
+        if (t - kPeerLag >= 0 && t - kPeerLag < nt) { mma2(false, m2_left == nt, m2_left == 1); --m2_left; }
       }
     }
   }
   // =========================================================================== epilogue warps
-  else if (warp >= 4) {
+  else if (warp < 4) {
+    setmaxnreg_dec<80>();      // TMEM allocator + spare warp: nothing to do until teardown
+  }
+  else if (warp < 12) {
+    setmaxnreg_inc<168>();
     const int e = warp - 4;
     const int q = warp & 3;       // TMEM lane quarter this warp may access
     const int h = e >> 2;         // which 64-column half of the S tile
     const int rrow = 32 * q + lane;
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-    const uint32_t peer_w = mapa(sm_w, peer);
-    const uint32_t peer_w_full = mapa(bar(BAR_W_FULL), peer);
     uint32_t ke = 0, item_cnt = 0;
+    Tracer tr; tr.init(e == 0 ? P.trace : nullptr, pair_id, crank, 2);
     for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
       SCB_PAIR_ITEM_SETUP();
       const int64_t gi = (int64_t)rb * 128 + rrow;
@@ -370,7 +443,9 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           ptx::named_bar_sync(1, kEpiThreads);
         }
+        if (lane == 0) tr.rec(40, ke);
         ptx::mbar_wait(bar(BAR_S_FULL + b), (ke >> 1) & 1u, 300);
+        if (lane == 0) tr.rec(41, ke);
         ptx::tc_fence_after();
         const int64_t drow0 = (int64_t)rb * 128 + 32 * q + P.diag_off;
         const bool diag_here = (drow0 < col0 + 64) && (drow0 + 32 > col0);
@@ -430,19 +505,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar(BAR_G_FULL + b));
-        // ---- peer copy: K-major SW128 image in the peer's Wrecv (once the peer has consumed the previous one)
-        ptx::mbar_wait(bar(BAR_W_EMPTY), (ke & 1u) ^ 1u, 310);
-        {
-          const uint32_t row_addr = peer_w + (uint32_t)h * kSlotBytes + (uint32_t)rrow * 128u;
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            st_cluster_v4(row_addr + (uint32_t)((u ^ (rrow & 7)) << 4), packed[4 * u], packed[4 * u + 1], packed[4 * u + 2],
-                          packed[4 * u + 3]);
-          fence_proxy_async_all();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(peer_w_full);
-        }
+        if (lane == 0) { ptx::mbar_arrive(bar(BAR_G_FULL + b)); tr.rec(42, ke); }
       }  // own tiles
 
       // ---- drain my half of the output accumulator
@@ -481,6 +544,50 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }  // items
   }
+  // =========================================================================== W senders
+  else {
+    setmaxnreg_dec<96>();
+    const int q = warp & 3;
+    const int rrow = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const uint32_t peer_w = mapa(sm_w, peer);
+    const uint32_t peer_w_full = mapa(bar(BAR_W_FULL), peer);
+    uint32_t kx = 0, item_cnt = 0;
+    Tracer tr; tr.init(q == 0 ? P.trace : nullptr, pair_id, crank, 3);
+    for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
+      SCB_PAIR_ITEM_SETUP();
+      for (int t = t_first; t < nt; t += 2, ++kx) {
+        const uint32_t b = kx & 1u;
+        ptx::mbar_wait(bar(BAR_G_FULL + b), (kx >> 1) & 1u, 400);
+        if (lane == 0) tr.rec(50, kx);
+        ptx::tc_fence_after();
+        uint32_t w0[32], w1[32];     // the two 64-column halves of my 32 rows of W (packed 16-bit pairs)
+        ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b, w0);
+        ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b + 64u, w1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(BAR_S_EMPTY + b));
+        // K-major SW128 image in the peer's Wrecv, once the peer has consumed the previous tile
+        ptx::mbar_wait(bar(BAR_W_EMPTY), (kx & 1u) ^ 1u, 410);
+        if (lane == 0) tr.rec(51, kx);
+        const uint32_t row_addr = peer_w + (uint32_t)rrow * 128u;
+        if (P.dbg & 1) {     // timing experiment: same handshake, 1/16 of the bytes
+          st_async_v4(row_addr, w0[0], w0[1], w0[2], w0[3], peer_w_full);
+          continue;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          st_async_v4(row_addr + (uint32_t)((u ^ (rrow & 7)) << 4), w0[4 * u], w0[4 * u + 1], w0[4 * u + 2], w0[4 * u + 3],
+                      peer_w_full);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          st_async_v4(row_addr + kSlotBytes + (uint32_t)((u ^ (rrow & 7)) << 4), w1[4 * u], w1[4 * u + 1], w1[4 * u + 2],
+                      w1[4 * u + 3], peer_w_full);
+        if (lane == 0) tr.rec(52, kx);
+      }
+    }
+  }
 #undef SCB_PAIR_ITEM_SETUP
 
   // =========================================================================== teardown
@@ -500,11 +607,16 @@ int scb_make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int D, int6
 
 namespace {
 
+unsigned long long* g_pair_trace = nullptr;
+int g_pair_dbg = 0;
+
 template <int MODE>
 int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                 PairParams P, cudaStream_t s) {
   if (nA == 0) return 0;
   P.nA = nA; P.nB = nB; P.D = D;
+  P.trace = g_pair_trace;
+  P.dbg = g_pair_dbg;
   P.kch = (D + 63) / 64;
   P.n_rb = (int)((nA + 127) / 128);
   P.n_jb = (int)((nB + 127) / 128);
@@ -512,12 +624,13 @@ int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
   SCB_CHECK_ARG(P.jparts >= 1 && P.jparts <= P.n_jb, SCB_E_ARG, "jparts=%d outside [1, %d]", P.jparts, P.n_jb);
   P.fmt = (dtype == SCB_BF16) ? 1 : 0;
   const int budget = 232448 - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
-  int nslots = (budget - (P.kch + 2) * kSlotBytes) / kSlotBytes;
+  const int n_astat = P.kch < kAStat ? P.kch : kAStat;
+  int nslots = (budget - (n_astat + 2) * kSlotBytes) / kSlotBytes;
   nslots &= ~1;
   if (nslots > kMaxSlots) nslots = kMaxSlots;
   SCB_CHECK_ARG(nslots >= 4, SCB_E_SHAPE, "not enough shared memory for the chunk ring (D=%d)", D);
   P.nslots = nslots;
-  const size_t smem = (size_t)(P.kch + 2 + nslots) * kSlotBytes + 3 * 1024;
+  const size_t smem = (size_t)(n_astat + 2 + nslots) * kSlotBytes + 3 * 1024;
 
   CUtensorMap tmA, tmB;
   int rc = scb_make_tmap_2d(&tmA, A, nA, D, ldA, dtype);
@@ -565,3 +678,10 @@ int scb_tc_pair_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll
   P.out = U; P.s0 = rq; P.s1 = rs;
   return launch_pair<M_LUNIF_GRAD>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
 }
+
+// debug: timeline buffer for the next pair launches (2 CTAs x 4 roles x 4096 events x 2 words of 8 bytes), or null
+extern "C" int scb_debug_pair_trace(void* buf) {
+  g_pair_trace = static_cast<unsigned long long*>(buf);
+  return 0;
+}
+int scb_tc_pair_set_dbg(int v) { g_pair_dbg = v; return 0; }

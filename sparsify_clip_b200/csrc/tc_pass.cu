@@ -592,7 +592,8 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
 
 }  // namespace
 
-int scb_tc_set_flags(int flags) { int o = g_tc_flags; g_tc_flags = flags; return o; }
+int scb_tc_pair_set_dbg(int);
+int scb_tc_set_flags(int flags) { int o = g_tc_flags; g_tc_flags = flags & 3; scb_tc_pair_set_dbg(flags >> 2); return o; }
 int scb_make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype) {
   return make_tmap(m, base, rows, D, ld, dtype);
 }
