@@ -143,6 +143,19 @@ int scb_lunif_grad_finalize(const float* U, int jparts, const float* rq, int npa
                             const void* X, int64_t ld, int dtype, float host_scale, const float* dev_scale,
                             int accumulate, float* dX, void* stream);
 
+/* Fused gradient finaliser of the composed loss (the ladder at sparsify_clip.py:775-938 adds the terms; here
+ * their gradients w.r.t. one operand are combined in a single pass, written in `out_dtype`):
+ *   dX[i,:] = gs * ( a_coef * ( sum_p a_out[p][i,:] + (e^{sc*diag_i - row_lse_i} + e^{sc*diag_i - col_lse_i} - 2) * Y[i,:] )
+ *                  + uc     * ( (sum_q rq[q][i]) * X[i,:] - sum_p u_out[p][i,:] )
+ *                  + l_coef * ( X[i,:] - Y[i,:] ) )
+ * gs = dev_scale ? *dev_scale : 1;  uc = u_coef * (u_dev_coef ? *u_dev_coef : 1).  a_out / u_out may be NULL
+ * (term absent); l_coef == 0 skips L_align.  X = the operand's rows, Y = the paired rows of the other modality. */
+int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
+                     const float* a_out, int a_jparts, const float* row_lse, const float* col_lse_rows,
+                     const float* diag, float scale, float a_coef, const float* u_out, int u_jparts,
+                     const float* rq, int rq_parts, float u_coef, const float* u_dev_coef, float l_coef,
+                     const float* dev_scale, void* dX, int out_dtype, int64_t ldOut, void* stream);
+
 /* sparsify_loss (sparsify_clip.py:166-176), forward: row partial sums of
  * (x_i.x_j - (2 delta_ij - 1))^2 over j; rs [jparts*nsub][nR]. */
 int scb_sparsify_sum_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,

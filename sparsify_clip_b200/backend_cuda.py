@@ -250,6 +250,41 @@ class CudaBackend:
                   "anchor_grad_finalize")
         return dA, (self.sum(ws) if want_ws else None)
 
+    def anchor_grad_pass(self, A, Ball, scale, row_lse, col_lse_all, diag_off, want_ws):
+        """The recompute sweep alone (no finaliser): {'out': [jparts, nA, D] fp32 partials, 'jparts', 'ws': 0-dim or None}."""
+        nA, D = A.shape
+        nB = Ball.shape[0]
+        path = self.path_for(A, Ball)
+        jp, nsub = self._plan(path, nA, nB, D, True, A.device)
+        out = torch.empty(jp, nA, D, dtype=torch.float32, device=A.device)
+        ws = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
+        with torch.cuda.device(A.device):
+            with self._Timed(self, "anchor_grad"):
+                check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0),
+                                                    _DT[A.dtype], float(scale), _ptr(row_lse), _ptr(col_lse_all),
+                                                    int(diag_off), jp, _ptr(out), _ptr(ws), path, self._stream()),
+                      "anchor_grad_pass")
+        self._count()
+        return {"out": out, "jparts": jp, "ws": self.sum(ws) if want_ws else None}
+
+    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None):
+        """dX = a_coef (sum_p out[p] + dcoef Y) + u_coef (rq X - sum_p U[p]) + l_coef (X - Y), one streaming pass.
+        anchor = dict(out, jparts, row_lse, col_lse_rows, diag, scale, coef); unif = dict(core, coef, dev_coef)."""
+        n, D = X.shape
+        dX = torch.empty(n, D, dtype=out_dtype, device=X.device)
+        a, u = anchor or {}, unif or {}
+        core = u.get("core") or {}
+        with torch.cuda.device(X.device):
+            check(self.lib.scb_grad_combine(
+                _ptr(X), _ptr(Y), n, D, X.stride(0), Y.stride(0) if Y is not None else 0, _DT[X.dtype],
+                _ptr(a.get("out")), int(a.get("jparts", 0)), _ptr(a.get("row_lse")), _ptr(a.get("col_lse_rows")),
+                _ptr(a.get("diag")), float(a.get("scale", 0.0)), float(a.get("coef", 0.0)),
+                _ptr(core.get("U")), int(core.get("jparts", 0)), _ptr(core.get("rq")), int(core.get("nparts", 0)),
+                float(u.get("coef", 0.0)), _ptr(u.get("dev_coef")), float(l_coef), _ptr(dev_scale),
+                _ptr(dX), _DT[out_dtype], dX.stride(0), self._stream()), "grad_combine")
+        self._count()
+        return dX
+
     def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None):
         """One sweep over the pairwise Gaussian potentials of the rows of Xr against Xall.
         Returns {'rs_sum': 0-dim sum_i sum_{j != i} w_ij, and, when need_grad, 'U', 'rq', ...}."""

@@ -272,6 +272,113 @@ __global__ void __launch_bounds__(kThreads) k_lunif_fin(const float* __restrict_
   });
 }
 
+// ------------------------------------------------------------------ fused gradient combine
+// One pass over an operand that applies every term of the composed loss at once:
+//   dX[i,:] = gs * ( a_coef * ( sum_p a_out[p][i,:] + dcoef_i * Y[i,:] )          anchor  (dcoef_i = P_ii + Q_ii - 2)
+//                  + u_coef * ( (sum_q rq[q][i]) * X[i,:] - sum_p u_out[p][i,:] )  L_unif
+//                  + l_coef * ( X[i,:] - Y[i,:] ) )                                L_align
+// Each thread owns 8 consecutive columns of one row (16-byte loads of every partial, one 16/32-byte store), so the
+// kernel streams at HBM speed; the per-row scalars are recomputed per thread (a few L1-resident loads).
+struct CombineArgs {
+  const void* X; const void* Y; int64_t n; int D; int64_t ldX, ldY; int dtype;
+  const float* a_out; int a_jparts; const float* row_lse; const float* col_lse_rows; const float* diag; float scale;
+  float a_coef;
+  const float* u_out; int u_jparts; const float* rq; int rq_parts; float u_coef; const float* u_dev_coef;
+  float l_coef;
+  const float* dev_scale;
+  void* dX; int out_dtype; int64_t ldOut;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_grad_combine(const CombineArgs a) {
+  constexpr int W = VEC ? 8 : 1;
+  const int per_row = (a.D + W - 1) / W;
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = idx / per_row;
+  if (row >= a.n) return;
+  const int d = (int)(idx - row * per_row) * W;
+  float x[8], y[8], g[8];
+  const bool need_y = (a.a_out != nullptr) || (a.l_coef != 0.f);
+  if (VEC) {
+    scb_ld8(a.X, a.dtype, row * a.ldX + d, x);
+    if (need_y) scb_ld8(a.Y, a.dtype, row * a.ldY + d, y);
+  } else {
+    x[0] = scb_ld(a.X, a.dtype, row * a.ldX + d);
+    y[0] = need_y ? scb_ld(a.Y, a.dtype, row * a.ldY + d) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) g[i] = a.l_coef != 0.f ? a.l_coef * (x[i] - y[i]) : 0.f;
+  const int64_t o = row * (int64_t)a.D + d;
+  if (a.a_out) {
+    const float sii = a.scale * __ldg(a.diag + row);
+    const float dcoef = expf(sii - __ldg(a.row_lse + row)) + expf(sii - __ldg(a.col_lse_rows + row)) - 2.f;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < W; ++i) acc[i] = dcoef * y[i];
+    for (int p = 0; p < a.a_jparts; ++p) {
+      const float* src = a.a_out + (int64_t)p * a.n * a.D + o;
+      if (VEC) {
+        const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src)), v1 = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+        acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+        acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
+      } else {
+        acc[0] += __ldcs(src);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) g[i] = fmaf(a.a_coef, acc[i], g[i]);
+  }
+  if (a.u_out) {
+    const float uc = a.u_dev_coef ? a.u_coef * __ldg(a.u_dev_coef) : a.u_coef;
+    float r = 0.f;
+    for (int q = 0; q < a.rq_parts; ++q) r += __ldg(a.rq + (int64_t)q * a.n + row);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < W; ++i) acc[i] = r * x[i];
+    for (int p = 0; p < a.u_jparts; ++p) {
+      const float* src = a.u_out + (int64_t)p * a.n * a.D + o;
+      if (VEC) {
+        const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src)), v1 = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+        acc[0] -= v0.x; acc[1] -= v0.y; acc[2] -= v0.z; acc[3] -= v0.w;
+        acc[4] -= v1.x; acc[5] -= v1.y; acc[6] -= v1.z; acc[7] -= v1.w;
+      } else {
+        acc[0] -= __ldcs(src);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) g[i] = fmaf(uc, acc[i], g[i]);
+  }
+  if (a.dev_scale) {
+    const float gs = __ldg(a.dev_scale);
+#pragma unroll
+    for (int i = 0; i < W; ++i) g[i] *= gs;
+  }
+  const int64_t oo = row * a.ldOut + d;
+  if (VEC) {
+    if (a.out_dtype == SCB_F32) {
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.dX) + oo);
+      dst[0] = make_float4(g[0], g[1], g[2], g[3]);
+      dst[1] = make_float4(g[4], g[5], g[6], g[7]);
+    } else {
+      uint4 pk;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (a.out_dtype == SCB_BF16) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(g[2 * i], g[2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+          __half2 h = __floats2half2_rn(g[2 * i], g[2 * i + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.dX) + oo) = pk;
+    }
+  } else {
+    scb_st(a.dX, a.out_dtype, oo, g[0]);
+  }
+}
+
 }  // namespace
 
 // ============================================================================ C ABI
@@ -412,5 +519,29 @@ extern "C" int scb_lunif_grad_finalize(const float* U, int jparts, const float* 
   else
     k_lunif_fin<false><<<row_grid(n), kThreads, 0, s>>>(U, jparts, rq, nparts_rq, n, D, X, ld, dtype, host_scale, dev_scale, accumulate, dX);
   SCB_CHECK_LAUNCH("lunif_grad_finalize");
+  return 0;
+}
+
+extern "C" int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
+                                const float* a_out, int a_jparts, const float* row_lse, const float* col_lse_rows,
+                                const float* diag, float scale, float a_coef, const float* u_out, int u_jparts,
+                                const float* rq, int rq_parts, float u_coef, const float* u_dev_coef, float l_coef,
+                                const float* dev_scale, void* dX, int out_dtype, int64_t ldOut, void* stream) {
+  SCB_COMMON_CHECKS(X && dX, n, D, dtype);
+  SCB_CHECK_ARG(scb_dtype_ok(out_dtype) && ldOut >= D, SCB_E_ARG, "grad_combine: bad output layout");
+  SCB_CHECK_ARG(!a_out || (Y && row_lse && col_lse_rows && diag && a_jparts > 0), SCB_E_ARG, "grad_combine: anchor term");
+  SCB_CHECK_ARG(!u_out || (rq && rq_parts > 0 && u_jparts > 0), SCB_E_ARG, "grad_combine: L_unif term");
+  SCB_CHECK_ARG(l_coef == 0.f || Y, SCB_E_ARG, "grad_combine: L_align term needs Y");
+  if (n == 0) return 0;
+  CombineArgs a{X, Y, n, D, ldX, ldY, dtype, a_out, a_jparts, row_lse, col_lse_rows, diag, scale, a_coef, u_out, u_jparts,
+                rq, rq_parts, u_coef, u_dev_coef, l_coef, dev_scale, dX, out_dtype, ldOut};
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = vec_ok(X, ldX, D) && (!Y || vec_ok(Y, ldY, D)) && scb_aligned16(dX) && ldOut % 8 == 0;
+  const int per_row = vec ? D / 8 : D;
+  const int64_t total = n * per_row;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (vec) k_grad_combine<true><<<grid, 256, 0, s>>>(a);
+  else k_grad_combine<false><<<grid, 256, 0, s>>>(a);
+  SCB_CHECK_LAUNCH("grad_combine");
   return 0;
 }

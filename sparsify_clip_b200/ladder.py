@@ -10,9 +10,10 @@ get_alpha).  Behaviour is reproduced AS CODED:
     centroid variant is available as loss_type "...BETA*lunif(centroids)[intended]".
   * an unknown loss_type is an error (the reference dies at loss.item() one line later).
 """
-from .losses import contrastive_loss, lalign_loss, lunif_loss, normalized_centroids, centroid_operand_dtype
+from .losses import (contrastive_loss, lalign_loss, lunif_loss, normalized_centroids, centroid_operand_dtype,
+                     fused_terms_loss)
 
-__all__ = ["get_beta", "get_alpha", "ladder_weights", "compose_loss", "weighted_loss", "LOSS_TYPES"]
+__all__ = ["get_beta", "get_alpha", "ladder_weights", "compose_loss", "weighted_loss", "set_fused", "LOSS_TYPES"]
 
 
 def get_beta(current_step, total_steps, warmup_epoch=20, decay_epoch=50):
@@ -76,8 +77,21 @@ def ladder_weights(config, epoch, current_batch, t_total):
     return out
 
 
+_fuse = True
+
+
+def set_fused(flag):
+    """Evaluate centroid-free compositions as one fused autograd node (default) or term by term."""
+    global _fuse
+    prev, _fuse = _fuse, bool(flag)
+    return prev
+
+
 def weighted_loss(image_embeds, text_embeds, temperature, w, *, group=None):
     """sum of the selected terms; a zero weight skips the kernel (its gradient is exactly 0)."""
+    if _fuse and w["unif_cen"] == 0.0 and (w["anchor"] != 0.0 or w["align"] != 0.0 or w["unif_img"] != 0.0 or w["unif_txt"] != 0.0):
+        return fused_terms_loss(image_embeds, text_embeds, temperature, w["anchor"], w["align"], w["unif_img"],
+                                w["unif_txt"], group=group)
     loss = None
 
     def add(acc, wt, term):

@@ -24,7 +24,7 @@ from .backend_cuda import get_backend
 __all__ = [
     "contrastive_loss", "lunif_loss", "lalign_loss", "compute_centroids_only", "compute_centroids",
     "sparsify_loss", "random_alignment_loss", "contrastive_loss_roberta", "centroid_alignment_loss",
-    "normalized_centroids", "l2_normalize", "operand_dtype", "centroid_operand_dtype",
+    "normalized_centroids", "l2_normalize", "operand_dtype", "centroid_operand_dtype", "fused_terms_loss",
 ]
 
 
@@ -169,6 +169,116 @@ class _LunifFn(torch.autograd.Function):
 
 def lunif_loss(x, t=2, *, group=None, mma_dtype=None):
     return _LunifFn.apply(x, t, _resolve_group(group), mma_dtype)
+
+
+# ----------------------------------------------------------------------------- fused composition
+class _FusedTermsFn(torch.autograd.Function):
+    """w_a * contrastive_loss(I, T, tau) + w_l * lalign_loss(I, T) + w_i * lunif_loss(I) + w_t * lunif_loss(T)
+    (the compositions of sparsify_clip.py:778-938 that do not involve centroids) as ONE autograd node.
+
+    Same B x B passes as the separate functions; what is fused is everything around them: the per-term gradient
+    finalisers, the dtype casts and autograd's accumulation of the terms collapse into one streaming pass per
+    operand (scb_grad_combine) that writes dI / dT directly in the input dtype.  The gradient is produced in
+    forward (L_unif yields it in the same sweep as its value anyway); backward multiplies by grad_output."""
+
+    @staticmethod
+    def forward(ctx, I, T, tau_t, tau_f, w_a, w_l, w_i, w_t, t_unif, group):
+        be = get_backend()
+        I, T = _common(I, T)
+        Ip, Tp = be.prep(I), be.prep(T)
+        rank, ws = _world(group)
+        n, D = Ip.shape
+        B = n * ws
+        off = rank * n
+        need_I, need_T, need_tau = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need = need_I or need_T
+        I_all = T_all = None
+        if w_a != 0.0 or w_i != 0.0:
+            I_all = _all_gather_rows(Ip, group)
+        if w_a != 0.0 or w_t != 0.0:
+            T_all = _all_gather_rows(Tp, group)
+        loss = torch.zeros((), dtype=torch.float32, device=Ip.device)
+        an_I = an_T = None
+        dtau = None
+        if w_a != 0.0:
+            tau = float(tau_t) if tau_t is not None else float(tau_f)
+            scale = 1.0 / tau
+            r = be.lse(Ip, T_all, scale)
+            c = be.lse(Tp, I_all, scale)
+            diag = be.row_dot(Ip, Tp)
+            sdiag = be.sum(diag)
+            part = be.sum(r) + be.sum(c) - (2.0 * scale) * sdiag
+            _all_reduce_(part, group)
+            loss = loss + (w_a / (2.0 * B)) * part
+            if need or need_tau:
+                r_all, c_all = _all_gather_rows(r, group), _all_gather_rows(c, group)
+                coef = w_a * scale / (2.0 * B)
+                if need_I or need_tau:
+                    p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
+                    an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef)
+                    if need_tau:
+                        tpart = p["ws"] - 2.0 * sdiag
+                        _all_reduce_(tpart, group)
+                        dt, dev, shp = tau_t.dtype, tau_t.device, tau_t.shape
+                        dtau = (tpart * (-(w_a * scale * scale) / (2.0 * B))).to(device=dev, dtype=dt).reshape(shp)
+                if need_T:
+                    p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
+                    an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
+        un_I = un_T = None
+        for (wu, Xp, X_all, needx, which) in ((w_i, Ip, I_all, need_I, "I"), (w_t, Tp, T_all, need_T, "T")):
+            if wu == 0.0:
+                continue
+            core = be.lunif_core(Xp, X_all, float(t_unif), off, needx)
+            ssum = _all_reduce_(core["rs_sum"], group) * 0.5
+            loss = loss + wu * torch.log(ssum / (B * (B - 1) / 2.0))
+            if needx:
+                u = dict(core=core, coef=wu * (-2.0 * float(t_unif)), dev_coef=torch.reciprocal(ssum).contiguous())
+                if which == "I":
+                    un_I = u
+                else:
+                    un_T = u
+        if w_l != 0.0:
+            lpart = _all_reduce_(be.sum(be.lalign_rows(Ip, Tp)), group)
+            loss = loss + (w_l / B) * lpart
+        dI = dT = None
+        lc = 2.0 * w_l / B
+        if need_I:
+            dI = be.grad_combine(Ip, Tp, I.dtype if I.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32,
+                                 anchor=an_I, unif=un_I, l_coef=lc)
+        if need_T:
+            dT = be.grad_combine(Tp, Ip, T.dtype if T.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32,
+                                 anchor=an_T, unif=un_T, l_coef=lc)
+        ctx.in_dtypes = (I.dtype, T.dtype)
+        ctx.has = (dI is not None, dT is not None, dtau is not None)
+        ctx.save_for_backward(*[x for x in (dI, dT, dtau) if x is not None])
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        saved = list(ctx.saved_tensors)
+        g = _gout32(gout)
+        outs = []
+        for i, has in enumerate(ctx.has):
+            if not has:
+                outs.append(None)
+                continue
+            x = saved.pop(0)
+            if i < 2:
+                outs.append((x * g.to(x.dtype)).to(ctx.in_dtypes[i]))
+            else:
+                outs.append((x * g.to(device=x.device, dtype=x.dtype)))
+        return outs[0], outs[1], outs[2], None, None, None, None, None, None, None
+
+
+def fused_terms_loss(image_embeds, text_embeds, temperature=0.07, w_anchor=1.0, w_align=0.0, w_unif_img=0.0,
+                     w_unif_txt=0.0, t=2, *, group=None):
+    """w_anchor * contrastive_loss + w_align * lalign_loss + w_unif_img * lunif_loss(I) + w_unif_txt * lunif_loss(T),
+    evaluated as one fused autograd node (see _FusedTermsFn).  Zero weights skip their kernels."""
+    group = _resolve_group(group)
+    tt = temperature if isinstance(temperature, torch.Tensor) else None
+    tf = None if tt is not None else float(temperature)
+    return _FusedTermsFn.apply(image_embeds, text_embeds, tt, tf, float(w_anchor), float(w_align), float(w_unif_img),
+                               float(w_unif_txt), t, group)
 
 
 # ----------------------------------------------------------------------------- L_align

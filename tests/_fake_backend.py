@@ -60,6 +60,31 @@ class FakeBackend:
         dA = host_scale * dev_scale.double() * (Wd @ Ball + dcoef[:, None] * V_rows)
         return dA, ws
 
+    def anchor_grad_pass(self, A, Ball, scale, row_lse, col_lse_all, diag_off, want_ws):
+        G0 = A @ Ball.t()
+        S = scale * G0
+        W = torch.exp(S - row_lse[:, None]) + torch.exp(S - col_lse_all[None, :])
+        ws = (W * G0).sum() if want_ws else None
+        idx = torch.arange(A.shape[0])
+        W[idx, idx + diag_off] = 0
+        return {"out": (W @ Ball)[None], "jparts": 1, "ws": ws}
+
+    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None):
+        g = l_coef * (X - Y) if l_coef != 0.0 else torch.zeros_like(X)
+        if anchor:
+            sii = anchor["scale"] * anchor["diag"]
+            dcoef = torch.exp(sii - anchor["row_lse"]) + torch.exp(sii - anchor["col_lse_rows"]) - 2
+            g = g + anchor["coef"] * (anchor["out"].sum(0) + dcoef[:, None] * Y)
+        if unif:
+            core = unif["core"]
+            U = core["U"] if core["U"].dim() == 2 else core["U"].sum(0)
+            rq = core["rq"] if core["rq"].dim() == 1 else core["rq"].sum(0)
+            uc = unif["coef"] * (unif["dev_coef"].double() if unif.get("dev_coef") is not None else 1.0)
+            g = g + uc * (rq[:, None] * X - U)
+        if dev_scale is not None:
+            g = g * dev_scale.double()
+        return g.to(out_dtype)
+
     def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None):
         n = (Xall * Xall).sum(1)
         nr = (Xr * Xr).sum(1)

@@ -85,7 +85,7 @@ def test_fp32_exact_path_matches_golden(name):
     _check_against(z, got, LOSS_RTOL, GRAD_RTOL["exact"])
 
 
-@pytest.mark.parametrize("tc_flags", [0, 1])
+@pytest.mark.parametrize("tc_flags", [0, 1, 3])      # smem / TMEM weight tile; 3 = CTA-pair gradient kernel (256 < D <= 512)
 @pytest.mark.parametrize("name", [n for n in CASES if bool(_golden.load(n)["bf16_exact"])])
 def test_bf16_tensor_core_path_matches_golden(name, tc_flags):
     """bf16-exact inputs -> TMA + tcgen05 kernels.  Inputs are handed over as fp32 tensors holding bf16-exact
@@ -227,3 +227,35 @@ def test_ladder_on_gpu_matches_oracle():
             ref, dI, dT, _, terms = cf.compose_loss(cfg, I.numpy(), T.numpy(), 0.1, epoch, step, 1000)
             assert abs(loss.item() - ref) <= LOSS_RTOL * sum(abs(v) for v in terms.values()), (lt, epoch)
             assert np.linalg.norm(Ig.grad.double().cpu().numpy() - dI) <= 1e-5 * max(np.linalg.norm(dI), 1e-30), (lt, epoch)
+
+
+@pytest.mark.parametrize("B,D,dtype", [(384, 512, torch.bfloat16), (200, 128, torch.float32), (1000, 768, torch.float16)])
+def test_fused_composition_equals_the_sum_of_its_terms(B, D, dtype):
+    """weighted_loss through the fused autograd node (scb_grad_combine) vs the term-by-term composition: same passes,
+    so the loss agrees to fp32 rounding and the gradients to the rounding of the output dtype."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    I0 = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device="cuda"), dim=-1)
+    T0 = torch.nn.functional.normalize(I0 + 0.5 * torch.randn(B, D, generator=g, device="cuda"), dim=-1)
+    for w in (dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0),
+              dict(anchor=1.0, align=1.3, unif_img=0.1, unif_txt=0.1, unif_cen=0.0),
+              dict(anchor=0.0, align=0.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0),
+              dict(anchor=1.0, align=0.0, unif_img=0.0, unif_txt=0.0, unif_cen=0.0)):
+        res = []
+        for fused in (True, False):
+            prev = scb.set_fused(fused)
+            try:
+                I = I0.to(dtype).requires_grad_(True)
+                T = T0.to(dtype).requires_grad_(True)
+                tp = torch.nn.Parameter(torch.tensor(0.1))
+                loss = scb.weighted_loss(I, T, tp, w)
+                (loss * 4.0).backward()
+                res.append((loss.item(), I.grad.float(), T.grad.float(), None if tp.grad is None else tp.grad.item()))
+            finally:
+                scb.set_fused(prev)
+        (lf, dIf, dTf, dtf), (lm, dIm, dTm, dtm) = res
+        assert abs(lf - lm) <= 2e-6 * max(1.0, abs(lm)), (w, lf, lm)
+        tol = 1e-5 if dtype == torch.float32 else 8e-3          # one extra rounding per term in the modular path
+        for a, b in ((dIf, dIm), (dTf, dTm)):
+            assert ((a - b).norm() / b.norm().clamp_min(1e-30)).item() <= tol, (w, dtype)
+        if w["anchor"] != 0.0:
+            assert abs(dtf - dtm) <= 1e-5 * abs(dtm), (w, dtf, dtm)
