@@ -35,6 +35,7 @@ constexpr int kSlotBytes = 128 * 64 * 2;   // one [128 x 64] 16-bit chunk
 constexpr int kMaxSlots = 8;
 constexpr int kAStat = 6;                  // K-chunks of A resident in smem; the rest stream with the column tile
                                            // (frees ring slots: the ring, not the tensor pipe, was the bottleneck)
+constexpr int kSendPaceClk = 200;          // idle cycles between two 16-byte remote stores of a sender thread
 constexpr int kPeerLag = 3;                // MMA2 of a peer tile is issued this many steps after the tile (odd:
                                            // it lands on my own steps); hides epilogue + DSMEM latency of the peer
 constexpr uint32_t kTmemCols = 512;
@@ -51,7 +52,8 @@ struct PairParams {
   float* s0;   // anchor: ws ; lunif: rq     [jparts*4][nA]
   float* s1;   // lunif: rs
   unsigned long long* trace;   // debug timeline (scb_debug_pair_trace), normally null
-  int dbg;                     // timing experiments only (bit0: skip the W transfer -> WRONG results)
+  int dbg;                     // tuning/timing experiments: bit0 = send 1/16 of the W bytes (WRONG results);
+                               // bits 3.. = sender pace override in units of 50 cycles
 };
 
 // Debug timeline: cluster 0 records (tag, tile, clock64) per role; kTraceCap events per (CTA rank, role).
@@ -572,18 +574,28 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ptx::mbar_wait(bar(BAR_W_EMPTY), (kx & 1u) ^ 1u, 410);
         if (lane == 0) tr.rec(51, kx);
         const uint32_t row_addr = peer_w + (uint32_t)rrow * 128u;
+        // Pacing: a back-to-back burst of 64 remote stores per warp delays the TMA traffic of both SMs (measured:
+        // ~3000 cycles per tile pair); spreading the 32 KB over ~3000 cycles costs nothing (the peer consumes the
+        // tile kPeerLag steps later) and was the best of {0, 100, 200, 300, 400+} cycles per store.
+        const int pace = (P.dbg >> 3) ? (P.dbg >> 3) * 50 : kSendPaceClk;
         if (P.dbg & 1) {     // timing experiment: same handshake, 1/16 of the bytes
           st_async_v4(row_addr, w0[0], w0[1], w0[2], w0[3], peer_w_full);
           continue;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
+        {
           st_async_v4(row_addr + (uint32_t)((u ^ (rrow & 7)) << 4), w0[4 * u], w0[4 * u + 1], w0[4 * u + 2], w0[4 * u + 3],
                       peer_w_full);
+          if (pace) { const long long c0 = clock64(); while (clock64() - c0 < pace) {} }
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
+        {
           st_async_v4(row_addr + kSlotBytes + (uint32_t)((u ^ (rrow & 7)) << 4), w1[4 * u], w1[4 * u + 1], w1[4 * u + 2],
                       w1[4 * u + 3], peer_w_full);
+          if (pace) { const long long c0 = clock64(); while (clock64() - c0 < pace) {} }
+        }
         if (lane == 0) tr.rec(52, kx);
       }
     }

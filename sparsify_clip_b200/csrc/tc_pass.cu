@@ -534,7 +534,7 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld,
   return 0;
 }
 
-int g_tc_flags = 1;   // bit0: weight tile in TMEM (TS-mode MMA2) -- measured faster than the smem variant
+int g_tc_flags = 3;   // bit0: weight tile in TMEM (TS-mode MMA2) -- measured faster than the smem variant
                       // bit1: CTA-pair kernel (tc_pair.cu) for the gradient passes when 256 < D <= 512
 
 template <int MODE>
