@@ -48,6 +48,18 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        k = d["per_launch_dram_bytes"][d["dominant"]]
+        return float(k["read"] + k["write"])
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -293,8 +305,13 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_tc_pass<MODE> (2 LSE + 2 anchor-grad + 2 lunif launches per step)",
+                         "traffic": measured_traffic(), "peak_source": peak_src,
+                         "kernel": "the six B x B pass launches of a step: 2 x k_tc_pass<LSE>, 2 x k_tc_pair<anchor-grad>, "
+                                   "2 x k_tc_pair<lunif> (dominant: k_tc_pair<lunif>; `traffic` = its DRAM bytes per launch)",
+                         "dominant_kernel": {"name": "k_tc_pair<M_LUNIF_GRAD>", "algorithmic_flops_per_launch": 4.0 * B * B * D / world,
+                                             "ms_per_launch": per.get("lunif", [0.0]) and sum(per["lunif"]) / len(per["lunif"]),
+                                             "achieved_tflops": (4.0 * B * B * D / world) / max(1e-9, sum(per["lunif"]) / len(per["lunif"]) * 1e-3) / 1e12
+                                             if per.get("lunif") else None},
                          "algorithmic_flops_per_step": flops_alg, "passes_ms_per_step": pass_ms,
                          "per_pass_ms": {k: sum(v) / prof_steps for k, v in per.items()},
                          "whole_step_frac": flops_alg / world / (ms_per_step * 1e-3) / 1e12 / peak},

@@ -113,7 +113,12 @@ def test_bf16_tensor_core_path_matches_golden(name, tc_flags):
 
 @pytest.mark.parametrize("B,D,tau,kind", [(127, 512, 0.1, "corr"), (129, 1024, 0.07, "cluster"), (1000, 64, 1.0, "corr"),
                                            (4096, 512, 0.1, "corr"), (300, 768, 0.01, "cluster"), (2, 64, 0.1, "iid"),
-                                           (3, 8, 0.5, "iid")])
+                                           (3, 8, 0.5, "iid"),
+                                           # CTA-pair gradient kernel (256 < D <= 512): every K-chunk count 5..8 (padding
+                                           # slots, odd output halves), D tails, odd / single tile counts, row tails
+                                           (640, 320, 0.1, "corr"), (385, 384, 0.07, "cluster"), (1300, 448, 0.1, "corr"),
+                                           (129, 264, 0.1, "iid"), (128, 512, 0.1, "corr"), (2100, 456, 0.05, "cluster"),
+                                           (5000, 512, 0.1, "corr")])
 def test_tensor_core_path_vs_oracle_on_seeded_inputs(B, D, tau, kind):
     from oracle.make_golden import make_inputs
     I, T = make_inputs(kind, B, D, seed=B + D)
