@@ -51,6 +51,14 @@ def _all_gather_rows(x, group):
     return out
 
 
+def _all_gather_rows_async(x, group):
+    """-> (gathered tensor, work handle); the caller waits on the handle before the first use."""
+    ws = dist.get_world_size(group)
+    x = x.contiguous()
+    out = torch.empty((ws * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    return out, dist.all_gather_into_tensor(out, x, group=group, async_op=True)
+
+
 def _all_reduce_(x, group):
     if group is not None:
         dist.all_reduce(x, group=group)
@@ -190,16 +198,28 @@ class _FusedTermsFn(torch.autograd.Function):
         n, D = Ip.shape
         B = n * ws
         off = rank * n
+        dev = Ip.device
         need_I, need_T, need_tau = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         need = need_I or need_T
-        I_all = T_all = None
-        if w_a != 0.0 or w_i != 0.0:
-            I_all = _all_gather_rows(Ip, group)
-        if w_a != 0.0 or w_t != 0.0:
-            T_all = _all_gather_rows(Tp, group)
-        loss = torch.zeros((), dtype=torch.float32, device=Ip.device)
+        # ---- exchange step 1: the operands (both gathers in flight together)
+        I_all, T_all, pending = Ip, Tp, []
+        if group is not None:
+            if w_a != 0.0 or w_i != 0.0:
+                I_all, h = _all_gather_rows_async(Ip, group)
+                pending.append(h)
+            if w_a != 0.0 or w_t != 0.0:
+                T_all, h = _all_gather_rows_async(Tp, group)
+                pending.append(h)
+        # scalar partial sums of this rank; ONE all-reduce for all of them at the end
+        #   0: anchor (sum r + sum c - 2/tau sum diag)   1: L_align   2, 3: L_unif row sums (I, T)   4: d/dtau
+        parts = torch.zeros(5, dtype=torch.float32, device=dev)
+        if w_l != 0.0:
+            parts[1] = be.sum(be.lalign_rows(Ip, Tp))
+        for h in pending:
+            h.wait()
         an_I = an_T = None
-        dtau = None
+        scale = 0.0
+        rc_pending = None
         if w_a != 0.0:
             tau = float(tau_t) if tau_t is not None else float(tau_f)
             scale = 1.0 / tau
@@ -207,47 +227,58 @@ class _FusedTermsFn(torch.autograd.Function):
             c = be.lse(Tp, I_all, scale)
             diag = be.row_dot(Ip, Tp)
             sdiag = be.sum(diag)
-            part = be.sum(r) + be.sum(c) - (2.0 * scale) * sdiag
-            _all_reduce_(part, group)
-            loss = loss + (w_a / (2.0 * B)) * part
-            if need or need_tau:
-                r_all, c_all = _all_gather_rows(r, group), _all_gather_rows(c, group)
-                coef = w_a * scale / (2.0 * B)
-                if need_I or need_tau:
-                    p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
-                    an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef)
-                    if need_tau:
-                        tpart = p["ws"] - 2.0 * sdiag
-                        _all_reduce_(tpart, group)
-                        dt, dev, shp = tau_t.dtype, tau_t.device, tau_t.shape
-                        dtau = (tpart * (-(w_a * scale * scale) / (2.0 * B))).to(device=dev, dtype=dt).reshape(shp)
-                if need_T:
-                    p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
-                    an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
+            parts[0] = be.sum(r) + be.sum(c) - (2.0 * scale) * sdiag
+            r_all, c_all = r, c
+            if group is not None and (need or need_tau):
+                # exchange step 2: both LSE vectors in one gather, overlapped with the L_unif sweeps below
+                rc = torch.stack((r, c)).contiguous()
+                rc_all = torch.empty((ws, 2, n), dtype=torch.float32, device=dev)
+                rc_pending = (dist.all_gather_into_tensor(rc_all, rc, group=group, async_op=True), rc_all)
         un_I = un_T = None
-        for (wu, Xp, X_all, needx, which) in ((w_i, Ip, I_all, need_I, "I"), (w_t, Tp, T_all, need_T, "T")):
+        cores = {}
+        for (wu, Xp, X_all, needx, which, slot) in ((w_i, Ip, I_all, need_I, "I", 2), (w_t, Tp, T_all, need_T, "T", 3)):
             if wu == 0.0:
                 continue
             core = be.lunif_core(Xp, X_all, float(t_unif), off, needx)
-            ssum = _all_reduce_(core["rs_sum"], group) * 0.5
-            loss = loss + wu * torch.log(ssum / (B * (B - 1) / 2.0))
+            parts[slot] = core["rs_sum"]
+            cores[which] = (core, wu, needx)
+        if w_a != 0.0 and (need or need_tau):
+            if rc_pending is not None:
+                rc_pending[0].wait()
+                r_all = rc_pending[1][:, 0, :].reshape(-1)
+                c_all = rc_pending[1][:, 1, :].reshape(-1)
+            coef = w_a * scale / (2.0 * B)
+            if need_I or need_tau:
+                p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
+                an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef)
+                if need_tau:
+                    parts[4] = p["ws"] - 2.0 * sdiag
+            if need_T:
+                p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
+                an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
+        # ---- exchange step 3: every scalar in one all-reduce
+        _all_reduce_(parts, group)
+        loss = (w_a / (2.0 * B)) * parts[0] + (w_l / B) * parts[1]
+        for which, (core, wu, needx) in cores.items():
+            ssum = parts[2 if which == "I" else 3] * 0.5
+            loss = loss + wu * torch.log(ssum / (B * (B - 1) / 2.0))      # B == 1 -> nan, as the reference
             if needx:
-                u = dict(core=core, coef=wu * (-2.0 * float(t_unif)), dev_coef=torch.reciprocal(ssum).contiguous())
+                u = dict(core=core, coef=wu * (-2.0 * float(t_unif)), dev_coef=torch.reciprocal(ssum).reshape(1).contiguous())
                 if which == "I":
                     un_I = u
                 else:
                     un_T = u
-        if w_l != 0.0:
-            lpart = _all_reduce_(be.sum(be.lalign_rows(Ip, Tp)), group)
-            loss = loss + (w_l / B) * lpart
+        dtau = None
+        if need_tau and w_a != 0.0:
+            dt, tdev, shp = tau_t.dtype, tau_t.device, tau_t.shape
+            dtau = (parts[4] * (-(w_a * scale * scale) / (2.0 * B))).to(device=tdev, dtype=dt).reshape(shp)
         dI = dT = None
         lc = 2.0 * w_l / B
+        okdt = (torch.float32, torch.bfloat16, torch.float16)
         if need_I:
-            dI = be.grad_combine(Ip, Tp, I.dtype if I.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32,
-                                 anchor=an_I, unif=un_I, l_coef=lc)
+            dI = be.grad_combine(Ip, Tp, I.dtype if I.dtype in okdt else torch.float32, anchor=an_I, unif=un_I, l_coef=lc)
         if need_T:
-            dT = be.grad_combine(Tp, Ip, T.dtype if T.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32,
-                                 anchor=an_T, unif=un_T, l_coef=lc)
+            dT = be.grad_combine(Tp, Ip, T.dtype if T.dtype in okdt else torch.float32, anchor=an_T, unif=un_T, l_coef=lc)
         ctx.in_dtypes = (I.dtype, T.dtype)
         ctx.has = (dI is not None, dT is not None, dtau is not None)
         ctx.save_for_backward(*[x for x in (dI, dT, dtau) if x is not None])
