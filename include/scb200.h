@@ -109,6 +109,26 @@ int scb_lse_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, i
 /* lse[i] = natural-log LSE from nparts partials. */
 int scb_lse_combine(const float* part_m, const float* part_l, int nparts, int64_t n, float* lse, void* stream);
 
+/* Fused row + column LSE (tensor-core path): ONE sweep over S = scale * A.Bm^T yields the row partials of
+ * scb_lse_pass and, from the same tiles, partial column sums per 32-row strip:
+ *   sum_{i in strip p} 2^{y_ij} = col_sum[p][j] * 2^{col_ref[p][j/32]},  y = scale*log2(e) * A_i.Bm_j
+ * col_sum is [4*ceil(nA/128)][nB], col_ref [4*ceil(nA/128)][ceil(nB/32)]; part_m/part_l are [jparts*4][nA] here.  This replaces the second sweep
+ * (rows of S^T) of F.cross_entropy(logits.t(), ...) at sparsify_clip.py:129.  The partial sums are exact while the
+ * logits spread by less than 2^100 inside a 32 x 32 block; scb_lse2_spread_flag evaluates a sufficient norm bound ON
+ * THE DEVICE (flag = 1: not guaranteed) and scb_lse_pass_cond / scb_lse_combine_cond run the exact second sweep only
+ * when that flag is set -- no host synchronisation, CUDA-graph capturable. */
+int scb_lse2_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                  float scale, int jparts, float* part_m, float* part_l, float* col_ref, float* col_sum, void* stream);
+/* lse[j] = natural-log column LSE from the nparts = 4*ceil(nA/128) strip partials. */
+int scb_colstat_combine(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* lse, void* stream);
+/* *flag = (2 * scale * log2(e) * max_i |A_i| * max_j |B_j| >= 90) from the squared row norms (scb_row_sqnorm). */
+int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* sqnB, int64_t nB, float scale, int* flag, void* stream);
+/* scb_lse_pass / scb_lse_combine that do nothing unless *run_flag != 0 (device pointer). */
+int scb_lse_pass_cond(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                      float scale, int jparts, float* part_m, float* part_l, const int* run_flag, void* stream);
+int scb_lse_combine_cond(const float* part_m, const float* part_l, int nparts, int64_t n, float* lse, const int* run_flag,
+                         void* stream);
+
 /* Backward of the anchor loss w.r.t. the rows of A (sparsify_clip.py:110-132; the
  * recompute replaces autograd's saved B x B tensors):
  *   out[p][i,:]  = sum_{j in part p, j != i+diag_off} (e^{s_ij - row_lse_i} + e^{s_ij - col_lse_j}) Bm[j,:]

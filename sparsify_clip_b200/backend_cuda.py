@@ -33,17 +33,18 @@ def force_path(path):
     return prev
 
 
-def choose_jparts(n_rb, nsplit, n_jb, n_sm=148, max_parts=16):
+def choose_jparts(n_rb, nsplit, n_jb, n_sm=148, max_parts=16, overhead=1.0):
     """Split the column sweep so that (row blocks x column groups x parts) fills the SMs evenly.
 
-    cost model: rounds of `n_sm` concurrent work items x (tiles per item + 1 tile of prologue/drain).
+    cost model: rounds of `n_sm` concurrent work items x (tiles per item + `overhead` tiles of prologue/drain;
+    1 for the single-CTA kernels, 4 for the CTA-pair kernel).
     Host mirror of the planner inside the library (scb_pass_plan, csrc/api.cu), which is the one the
     backend uses; tests/test_host.py checks that the two agree.
     """
     best, best_cost = 1, None
     for jp in range(1, max(1, min(n_jb, max_parts)) + 1):
         rounds = math.ceil(n_rb * nsplit * jp / n_sm)
-        cost = rounds * (math.ceil(n_jb / jp) + 1.0)
+        cost = rounds * (math.ceil(n_jb / jp) + overhead)
         if best_cost is None or cost < best_cost - 1e-9:
             best, best_cost = jp, cost
     return best
@@ -225,6 +226,43 @@ class CudaBackend:
             self._count(2)
             check(self.lib.scb_lse_combine(_ptr(pm), _ptr(pl), jp * nsub, nA, _ptr(out), self._stream()), "lse_combine")
         return out
+
+    def lse_rows_cols(self, A, Bm, scale):
+        """(row LSE [nA], column LSE [nB]) of scale * A @ Bm^T.  Tensor-core path: ONE sweep (scb_lse2_pass) gives
+        both; the exact second sweep over Bm @ A^T is launched conditionally on a device-side norm bound (it returns
+        at once for unit-norm rows at tau >= 0.033).  Other paths: two sweeps."""
+        nA, D = A.shape
+        nB = Bm.shape[0]
+        path = self.path_for(A, Bm)
+        if path != PATH_TC:
+            return self.lse(A, Bm, scale), self.lse(Bm, A, scale)
+        dev = A.device
+        jp, nsub = self._plan(path, nA, nB, D, False, dev)
+        jp2, nsub2 = self._plan(path, nB, nA, D, False, dev)
+        n_strips = 4 * ((nA + 127) // 128)
+        f32 = dict(dtype=torch.float32, device=dev)
+        nsub = 4                      # the fused sweep runs 16 epilogue warps: four 32-column slices per tile
+        pm, pl = torch.empty(jp * nsub, nA, **f32), torch.empty(jp * nsub, nA, **f32)
+        cref, csum = torch.empty(n_strips, (nB + 31) // 32, **f32), torch.empty(n_strips, nB, **f32)
+        r, c = torch.empty(nA, **f32), torch.empty(nB, **f32)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        pm2, pl2 = torch.empty(jp2 * nsub2, nB, **f32), torch.empty(jp2 * nsub2, nB, **f32)
+        sqa, sqb = self.row_sqnorm(A), self.row_sqnorm(Bm)
+        st = self._stream()
+        with torch.cuda.device(dev):
+            check(self.lib.scb_lse2_spread_flag(_ptr(sqa), nA, _ptr(sqb), nB, float(scale), _ptr(flag), st), "lse2_spread_flag")
+            with self._Timed(self, "lse"):
+                check(self.lib.scb_lse2_pass(_ptr(A), nA, _ptr(Bm), nB, D, A.stride(0), Bm.stride(0), _DT[A.dtype],
+                                             float(scale), jp, _ptr(pm), _ptr(pl), _ptr(cref), _ptr(csum), st), "lse2_pass")
+            check(self.lib.scb_lse_combine(_ptr(pm), _ptr(pl), jp * nsub, nA, _ptr(r), st), "lse_combine")
+            check(self.lib.scb_colstat_combine(_ptr(cref), _ptr(csum), n_strips, nB, _ptr(c), st), "colstat_combine")
+            with self._Timed(self, "lse"):
+                check(self.lib.scb_lse_pass_cond(_ptr(Bm), nB, _ptr(A), nA, D, Bm.stride(0), A.stride(0), _DT[A.dtype],
+                                                 float(scale), jp2, _ptr(pm2), _ptr(pl2), _ptr(flag), st), "lse_pass_cond")
+            check(self.lib.scb_lse_combine_cond(_ptr(pm2), _ptr(pl2), jp2 * nsub2, nB, _ptr(c), _ptr(flag), st),
+                  "lse_combine_cond")
+        self._count(6)
+        return r, c
 
     def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off,
                     host_scale, dev_scale, want_ws):

@@ -8,7 +8,10 @@ int scb_simt_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_
 int scb_simt_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
                    int64_t, int, float*, float*, float*, cudaStream_t);
 int scb_simt_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
-int scb_tc_lse(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, cudaStream_t);
+int scb_tc_lse(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, const int*,
+               cudaStream_t);
+int scb_tc_lse2(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, float*, float*,
+                cudaStream_t);
 int scb_tc_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
                        int64_t, int, float*, float*, cudaStream_t);
 int scb_tc_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*, int64_t,
@@ -27,14 +30,15 @@ bool scb_tc_use_pair(int D, int grad);
   SCB_CHECK_ARG((jparts) >= 1, SCB_E_ARG, "%s: jparts must be >= 1", __func__)
 
 // Split the column sweep so that (row blocks x column groups x parts) fills the execution units evenly.
-// cost model: rounds of `n_units` concurrent work items x (tiles per item + 1 tile of prologue/drain).
-static int scb_choose_jparts(int64_t n_rb, int nsplit, int64_t n_jb, int n_units, int max_parts = 16) {
+// cost model: rounds of `n_units` concurrent work items x (tiles per item + `overhead` tiles of prologue/drain:
+// 1 for the single-CTA kernels, 4 for the CTA-pair kernel whose software pipeline is three steps deep).
+static int scb_choose_jparts(int64_t n_rb, int nsplit, int64_t n_jb, int n_units, double overhead = 1.0, int max_parts = 16) {
   int best = 1;
   double best_cost = -1.0;
   const int hi = (int)(n_jb < max_parts ? n_jb : max_parts);
   for (int jp = 1; jp <= (hi < 1 ? 1 : hi); ++jp) {
     const int64_t rounds = (n_rb * nsplit * jp + n_units - 1) / n_units;
-    const double cost = (double)rounds * ((double)((n_jb + jp - 1) / jp) + 1.0);
+    const double cost = (double)rounds * ((double)((n_jb + jp - 1) / jp) + overhead);
     if (best_cost < 0.0 || cost < best_cost - 1e-9) { best = jp; best_cost = cost; }
   }
   return best;
@@ -47,7 +51,7 @@ extern "C" int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, 
     const int kch = (D + 63) / 64;
     const int64_t n_rb = (nA + 127) / 128, n_jb = (nB + 127) / 128;
     if (scb_tc_use_pair(D, grad) && n_sm >= 2) {       // one work item per CTA pair, no column groups
-      *jparts = scb_choose_jparts(n_rb, 1, n_jb, n_sm / 2);
+      *jparts = scb_choose_jparts(n_rb, 1, n_jb, n_sm / 2, 4.0);
       *nsub = 4;
     } else {
       *jparts = scb_choose_jparts(n_rb, grad ? (kch + 3) / 4 : 1, n_jb, n_sm);
@@ -71,8 +75,27 @@ extern "C" int scb_lse_pass(const void* A, int64_t nA, const void* Bm, int64_t n
   SCB_CHECK_ARG((part_m && part_l) || nA == 0, SCB_E_ARG, "lse_pass: null output");
   SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "lse_pass: needs scale > 0 and nB > 0");
   cudaStream_t s = (cudaStream_t)stream;
-  return path == SCB_PATH_TC ? scb_tc_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, s)
+  return path == SCB_PATH_TC ? scb_tc_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, nullptr, s)
                              : scb_simt_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, s);
+}
+
+// the same sweep launched conditionally: the kernel returns at once unless *run_flag != 0 (tensor-core path only)
+extern "C" int scb_lse_pass_cond(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
+                                 int dtype, float scale, int jparts, float* part_m, float* part_l, const int* run_flag,
+                                 void* stream) {
+  SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, SCB_PATH_TC);
+  SCB_CHECK_ARG((part_m && part_l && run_flag) || nA == 0, SCB_E_ARG, "lse_pass_cond: null argument");
+  SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "lse_pass_cond: needs scale > 0 and nB > 0");
+  return scb_tc_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, run_flag, (cudaStream_t)stream);
+}
+
+extern "C" int scb_lse2_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                             float scale, int jparts, float* part_m, float* part_l, float* col_ref, float* col_sum,
+                             void* stream) {
+  SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, SCB_PATH_TC);
+  SCB_CHECK_ARG((part_m && part_l && col_ref && col_sum) || nA == 0, SCB_E_ARG, "lse2_pass: null output");
+  SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "lse2_pass: needs scale > 0 and nB > 0");
+  return scb_tc_lse2(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, col_ref, col_sum, (cudaStream_t)stream);
 }
 
 extern "C" int scb_anchor_grad_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,

@@ -217,6 +217,59 @@ __global__ void __launch_bounds__(256) k_lse_combine(const float* __restrict__ p
   lse[i] = (M + log2f(L)) * SCB_LN2;   // log2 domain -> natural log
 }
 
+// same, but only when *run_flag != 0 (the conditional column sweep behind the fused row+column LSE pass)
+__global__ void __launch_bounds__(256) k_lse_combine_cond(const float* __restrict__ pm, const float* __restrict__ pl, int nparts,
+                                                          int64_t n, float* __restrict__ lse, const int* __restrict__ run_flag) {
+  if (*run_flag == 0) return;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float M = -INFINITY;
+  for (int p = 0; p < nparts; ++p) M = fmaxf(M, pm[(int64_t)p * n + i]);
+  float L = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    const float m = pm[(int64_t)p * n + i];
+    if (m != -INFINITY) L += pl[(int64_t)p * n + i] * exp2f(m - M);
+  }
+  lse[i] = (M + log2f(L)) * SCB_LN2;
+}
+
+// column LSE from the per-strip partials of the fused pass: lse[j] = ln sum_p csum[p][j] 2^{cref[p][j/32]}
+__global__ void __launch_bounds__(256) k_colstat_combine(const float* __restrict__ cref, const float* __restrict__ csum,
+                                                         int nparts, int64_t n, float* __restrict__ lse) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const int64_t nref = (n + 31) / 32;
+  float M = -INFINITY, L = 0.f;
+  for (int p = 0; p < nparts; ++p) {          // online: one pass over the partials (coalesced across threads)
+    const float r = __ldg(cref + (int64_t)p * nref + (j >> 5));
+    const float v = __ldcs(csum + (int64_t)p * n + j);
+    if (r == -INFINITY || v == 0.f) continue;
+    if (r > M) { L *= exp2f(M - r); M = r; }
+    L += v * exp2f(r - M);
+  }
+  lse[j] = (M + log2f(L)) * SCB_LN2;
+}
+
+// flag = 1 when the logits can spread by more than `bound` (log2 units) inside one block of the fused pass:
+// 2 * scale * log2e * max_i |a_i| * max_j |b_j| >= bound   (sqn = squared row norms)
+__global__ void __launch_bounds__(1024) k_spread_flag(const float* __restrict__ sqnA, int64_t nA, const float* __restrict__ sqnB,
+                                                      int64_t nB, float scale, float bound, int* __restrict__ flag) {
+  __shared__ float sh[2][32];
+  float ma = 0.f, mb = 0.f;
+  for (int64_t i = threadIdx.x; i < nA; i += 1024) ma = fmaxf(ma, sqnA[i]);
+  for (int64_t i = threadIdx.x; i < nB; i += 1024) mb = fmaxf(mb, sqnB[i]);
+  ma = scb_warp_max(ma); mb = scb_warp_max(mb);
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = ma; sh[1][threadIdx.x >> 5] = mb; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    ma = scb_warp_max(sh[0][threadIdx.x]); mb = scb_warp_max(sh[1][threadIdx.x]);
+    if (threadIdx.x == 0) {
+      const float spread = 2.f * scale * SCB_LOG2E * sqrtf(ma) * sqrtf(mb);
+      *flag = (spread >= bound || !(spread == spread)) ? 1 : 0;      // NaN/inf norms -> take the exact sweep
+    }
+  }
+}
+
 // ------------------------------------------------------------------ gradient finalisers
 // dA[i,:] (+)= s * ( sum_p out[p][i,:] + dcoef_i * V[i,:] )
 template <bool VEC>
@@ -543,5 +596,30 @@ extern "C" int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, 
   if (vec) k_grad_combine<true><<<grid, 256, 0, s>>>(a);
   else k_grad_combine<false><<<grid, 256, 0, s>>>(a);
   SCB_CHECK_LAUNCH("grad_combine");
+  return 0;
+}
+
+extern "C" int scb_lse_combine_cond(const float* part_m, const float* part_l, int nparts, int64_t n, float* lse,
+                                    const int* run_flag, void* stream) {
+  SCB_CHECK_ARG(part_m && part_l && lse && run_flag && nparts > 0 && n >= 0, SCB_E_ARG, "lse_combine_cond: bad argument");
+  if (n == 0) return 0;
+  k_lse_combine_cond<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part_m, part_l, nparts, n, lse, run_flag);
+  SCB_CHECK_LAUNCH("lse_combine_cond");
+  return 0;
+}
+
+extern "C" int scb_colstat_combine(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* lse, void* stream) {
+  SCB_CHECK_ARG(col_ref && col_sum && lse && nparts > 0 && n >= 0, SCB_E_ARG, "colstat_combine: bad argument");
+  if (n == 0) return 0;
+  k_colstat_combine<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, lse);
+  SCB_CHECK_LAUNCH("colstat_combine");
+  return 0;
+}
+
+extern "C" int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* sqnB, int64_t nB, float scale, int* flag,
+                                    void* stream) {
+  SCB_CHECK_ARG(sqnA && sqnB && flag && nA >= 0 && nB >= 0 && scale > 0.f, SCB_E_ARG, "lse2_spread_flag: bad argument");
+  k_spread_flag<<<1, 1024, 0, (cudaStream_t)stream>>>(sqnA, nA, sqnB, nB, scale, 90.f, flag);
+  SCB_CHECK_LAUNCH("lse2_spread_flag");
   return 0;
 }

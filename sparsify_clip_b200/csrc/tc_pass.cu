@@ -25,15 +25,23 @@
 
 namespace {
 
-enum { M_LSE = 0, M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2, M_LUNIF_SUM = 3, M_SPARSIFY_SUM = 4 };
+enum { M_LSE = 0, M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2, M_LUNIF_SUM = 3, M_SPARSIFY_SUM = 4, M_LSE2 = 5 };
+// M_LSE2: row LSE as M_LSE plus, from the SAME S tiles, per-(row block, column) partial column sums
+//   colsum[strip][j] * 2^colref[strip][j/32] = sum_{i in 32-row strip} 2^{y_ij}   (y = scale*log2e * a_i.b_j)
+// so that the column LSE needs no second sweep over S^T.  Exact while the spread of y inside a 32 x 32 block stays
+// below kColBias (the caller checks a norm bound on the device and falls back to the second sweep otherwise).
 
 constexpr int kThreads = 384;
 constexpr int kEpiThreads = 256;
+// M_LSE2 runs 16 epilogue warps (32 columns each): its epilogue -- a 31-step shuffle butterfly per 32 x 32 block on
+// top of the exponentials -- is latency-bound with 8 warps (measured 0.97 ms vs 0.73 ms for the plain LSE sweep)
+__host__ __device__ constexpr int epi_warps(int mode) { return mode == 5 ? 16 : 8; }
 constexpr int kSlotBytes = 128 * 64 * 2;  // one [128 x 64] 16-bit tile ("chunk")
 constexpr int kPairBytes = 2 * kSlotBytes; // ring unit: two chunks under one full / one empty barrier
 constexpr int kMaxStages = 7;              // pair-slots
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColOut = 0, kColS0 = 256;
+constexpr float kColBias = 100.f;          // M_LSE2: exponent bias of the per-block column sums (log2 units)
 
 struct TcParams {
   int64_t nA, nB;
@@ -47,6 +55,9 @@ struct TcParams {
   float* out;  // [jparts][nA][D]
   float* s0;   // LSE: part_m ; anchor: ws ; lunif grad: rq ; sums: rs      [jparts*2][nA]
   float* s1;   // LSE: part_l ; lunif grad: rs
+  float* c0;   // LSE2: column reference   [n_rb*4][ceil(nB/32)]  (one per 32-row strip and 32-column chunk)
+  float* c1;   // LSE2: column partial sum [n_rb*4][nB]
+  const int* run_flag;   // when non-null the kernel does nothing unless *run_flag != 0 (device-side conditional fallback)
 };
 
 // barrier indices inside the barrier block
@@ -82,7 +93,7 @@ struct Ring {
 // KCH: number of 64-wide K chunks when known at compile time (8 for D = 512: the kc loops unroll and the
 // stationary-A descriptors become immediates), 0 = generic.
 template <int MODE, int KCH>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(128 + 32 * epi_warps(MODE), 1)
 k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams P) {
   constexpr bool GRAD = (MODE == M_ANCHOR_GRAD || MODE == M_LUNIF_GRAD);
   constexpr bool NEED_COLVEC = (MODE == M_ANCHOR_GRAD || MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM);
@@ -104,12 +115,15 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // generic pointers for the few plain loads/stores
   uint8_t* gen_base = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   float* cbuf = reinterpret_cast<float*>(gen_base + (sm_cbuf - smem_base));
+  if (P.run_flag && *P.run_flag == 0) return;         // conditional launch: nothing to do
   volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sm_tmem_ptr - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsplit_eff = GRAD ? P.nsplit : 1;
   const int n_items = P.n_rb * nsplit_eff * P.jparts;
-  const uint32_t s_empty_count = (GRAD && P.g_in_tmem) ? 1u : 8u;
+  constexpr int EW = epi_warps(MODE);        // epilogue warps
+  constexpr int CW = 512 / EW;               // S-tile columns per epilogue warp (64 or 32)
+  const uint32_t s_empty_count = (GRAD && P.g_in_tmem) ? 1u : (uint32_t)EW;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -300,7 +314,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   else if (warp >= 4) {
     const int e = warp - 4;
     const int q = warp & 3;       // TMEM lane quarter this warp may access
-    const int h = e >> 2;         // which 64-column half of the S tile
+    const int h = e >> 2;         // which CW-column slice of the S tile
     const int rrow = 32 * q + lane;
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     uint32_t gt = 0, item_cnt = 0;
@@ -317,13 +331,13 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       float rowc = 0.f;
       if (MODE == M_ANCHOR_GRAD) rowc = row_ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
       if (MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM) rowc = row_ok ? P.rowvec[gi] * P.p0 : 0.f;
-      float st0 = (MODE == M_LSE) ? -INFINITY : 0.f, st1 = 0.f;
+      float st0 = (MODE == M_LSE || MODE == M_LSE2) ? -INFINITY : 0.f, st1 = 0.f;
       const int64_t my_diag_col = gi + P.diag_off;  // column index that is "the diagonal" of this row
 
       for (int t = 0; t < nt; ++t, ++gt) {
         const uint32_t b = gt & 1u;
         const int jb = jb_lo + t;
-        const int64_t col0 = (int64_t)jb * 128 + 64 * h;     // first global column handled by this warp
+        const int64_t col0 = (int64_t)jb * 128 + CW * h;     // first global column handled by this warp
         const bool tile_partial = ((int64_t)jb * 128 + 128) > P.nB;
         if (NEED_COLVEC) {
           const int idx = e * 32 + lane;
@@ -339,21 +353,21 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ptx::tc_fence_after();
         // does the diagonal cross the 32x64 block this warp handles?
         const int64_t drow0 = (int64_t)rb * 128 + 32 * q + P.diag_off;
-        const bool diag_here = (drow0 < col0 + 64) && (drow0 + 32 > col0);
+        const bool diag_here = (drow0 < col0 + CW) && (drow0 + 32 > col0);
 
         uint32_t packed[32];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < CW / 32; ++cc) {
           uint32_t v[32];
-          ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b + 64u * h + 32u * cc, v);
+          ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b + (uint32_t)(CW * h) + 32u * cc, v);
           ptx::tmem_ld_wait();
           const int64_t cbase = col0 + 32 * cc;
-          const float* cb = cbuf + b * 128 + 64 * h + 32 * cc;
+          const float* cb = cbuf + b * 128 + CW * h + 32 * cc;
           const int dcol = diag_here ? (int)(my_diag_col - cbase) : -1;   // local index of the diagonal, if any
           // column tail (last column block only): neutralise the zero-filled columns once, up front
           if (tile_partial && MODE != M_LUNIF_GRAD && MODE != M_LUNIF_SUM) {
             const int nvalid = (int)min((int64_t)32, max((int64_t)0, P.nB - cbase));
-            const float dead = (MODE == M_LSE) ? -INFINITY : -1e30f;
+            const float dead = (MODE == M_LSE || MODE == M_LSE2) ? -INFINITY : -1e30f;
 #pragma unroll
             for (int c = 0; c < 32; ++c)
               if (c >= nvalid) v[c] = __float_as_uint(dead);
@@ -370,6 +384,42 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               st1 = st1 * scb_ex2(st0 - mnew) + sum;
               st0 = mnew;
             }
+          } else if (MODE == M_LSE2) {
+            // rows: online LSE with a chunk-local exponent reference; columns: the same exponentials, rescaled to
+            // the block reference rho = max over the 32 x 32 block, summed over the 32 rows by a shuffle butterfly
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) cmax = fmaxf(cmax, __uint_as_float(v[c]));
+            const float cm = cmax * P.p0;                       // -inf when every column of the chunk is dead
+            float ef[32];
+            float sum = 0.f;
+            const float cmf = (cmax != -INFINITY) ? cm : 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { ef[c] = scb_ex2(fmaf(__uint_as_float(v[c]), P.p0, -cmf)); sum += ef[c]; }
+            if (cmax != -INFINITY) {
+              const float mnew = fmaxf(st0, cm);
+              st1 = st1 * scb_ex2(st0 - mnew) + sum * scb_ex2(cm - mnew);
+              st0 = mnew;
+            }
+            const float rho = scb_warp_max(row_ok ? cm : -INFINITY);
+            const float f = (row_ok && cmax != -INFINITY) ? scb_ex2(cm - rho + kColBias) : 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) ef[c] *= f;
+            // butterfly: after the five steps lane L holds the sum over the 32 rows of column L of this chunk
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool up = (lane & sft) != 0;
+#pragma unroll
+              for (int k = 0; k < sft; ++k) {
+                const float mine = up ? ef[k + sft] : ef[k];
+                const float theirs = up ? ef[k] : ef[k + sft];
+                ef[k] = mine + __shfl_xor_sync(0xffffffffu, theirs, sft);
+              }
+            }
+            // one partial per (row block, 32-row strip): sums [n_rb*4][nB], references [n_rb*4][ceil(nB/32)]
+            const int64_t prow = (int64_t)rb * 4 + q;
+            if (cbase + lane < P.nB) P.c1[prow * P.nB + cbase + lane] = ef[0];
+            if (lane == 0 && cbase < P.nB) P.c0[prow * ((P.nB + 31) / 32) + (cbase >> 5)] = rho - kColBias;
           } else if (MODE == M_SPARSIFY_SUM) {
             if (!tile_partial && !diag_here) {
 #pragma unroll
@@ -482,8 +532,8 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) ptx::mbar_arrive(bar(BAR_OUT_EMPTY));
       }
       if (row_ok && split == 0) {
-        const int64_t o = ((int64_t)jp * 2 + h) * P.nA + gi;
-        if (MODE == M_LSE) { P.s0[o] = st0; P.s1[o] = st1; }
+        const int64_t o = ((int64_t)jp * (EW / 4) + h) * P.nA + gi;
+        if (MODE == M_LSE || MODE == M_LSE2) { P.s0[o] = st0; P.s1[o] = st1; }
         if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
         if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
         if (MODE == M_LUNIF_SUM) P.s1[o] = st1;
@@ -555,7 +605,7 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
   P.fmt = (dtype == SCB_BF16) ? 1 : 0;
   P.g_in_tmem = (GRAD && (g_tc_flags & 1)) ? 1 : 0;
   P.a_stationary = (P.kch <= 8) ? 1 : 0;
-  const int budget = 232448 - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
+  const int budget = 232448 - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/ ;
   const int fixed = (P.a_stationary ? P.kch * kSlotBytes : 0) + ((GRAD && !P.g_in_tmem) ? 2 * kSlotBytes : 0);
   int nstage = (budget - fixed) / kPairBytes;      // pair-slots of 32 KB
   if (nstage > kMaxStages) nstage = kMaxStages;
@@ -584,8 +634,9 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
   }
   const int n_items = P.n_rb * (GRAD ? P.nsplit : 1) * P.jparts;
   const int grid = n_items < num_sms ? n_items : num_sms;
-  if (P.kch == 8) k_tc_pass<MODE, 8><<<grid, kThreads, smem, s>>>(tmA, tmB, P);
-  else k_tc_pass<MODE, 0><<<grid, kThreads, smem, s>>>(tmA, tmB, P);
+  constexpr int threads = 128 + 32 * epi_warps(MODE);
+  if (P.kch == 8) k_tc_pass<MODE, 8><<<grid, threads, smem, s>>>(tmA, tmB, P);
+  else k_tc_pass<MODE, 0><<<grid, threads, smem, s>>>(tmA, tmB, P);
   SCB_CHECK_LAUNCH("tc_pass");
   return 0;
 }
@@ -608,10 +659,17 @@ int scb_tc_pair_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, 
                       int64_t, int, float*, float*, float*, cudaStream_t);
 
 int scb_tc_lse(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype, float scale,
-               int jparts, float* pm, float* pl, cudaStream_t s) {
+               int jparts, float* pm, float* pl, const int* run_flag, cudaStream_t s) {
   TcParams P{};
-  P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.diag_off = INT64_MIN / 2; P.s0 = pm; P.s1 = pl;
+  P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.diag_off = INT64_MIN / 2; P.s0 = pm; P.s1 = pl; P.run_flag = run_flag;
   return launch_tc<M_LSE>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
+}
+// rows AND columns from one sweep: col_sum [4 n_rb][nB], col_ref [4 n_rb][ceil(nB/32)], n_rb = ceil(nA / 128)
+int scb_tc_lse2(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype, float scale,
+                int jparts, float* pm, float* pl, float* col_ref, float* col_sum, cudaStream_t s) {
+  TcParams P{};
+  P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.diag_off = INT64_MIN / 2; P.s0 = pm; P.s1 = pl; P.c0 = col_ref; P.c1 = col_sum;
+  return launch_tc<M_LSE2>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
 }
 int scb_tc_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                        float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts, float* out,

@@ -92,8 +92,11 @@ class _AnchorFn(torch.autograd.Function):
         rank, ws = _world(group)
         n = Ip.shape[0]
         I_all, T_all = _all_gather_rows(Ip, group), _all_gather_rows(Tp, group)
-        r = be.lse(Ip, T_all, scale)                  # row LSE of the local rows of S
-        c = be.lse(Tp, I_all, scale)                  # column LSE of the local columns of S
+        if group is None:
+            r, c = be.lse_rows_cols(Ip, Tp, scale)    # row and column LSE from one sweep over S
+        else:
+            r = be.lse(Ip, T_all, scale)              # row LSE of the local rows of S
+            c = be.lse(Tp, I_all, scale)              # column LSE of the local columns of S
         diag = be.row_dot(Ip, Tp)
         part = be.sum(r) + be.sum(c) - (2.0 * scale) * be.sum(diag)
         _all_reduce_(part, group)
@@ -223,8 +226,11 @@ class _FusedTermsFn(torch.autograd.Function):
         if w_a != 0.0:
             tau = float(tau_t) if tau_t is not None else float(tau_f)
             scale = 1.0 / tau
-            r = be.lse(Ip, T_all, scale)
-            c = be.lse(Tp, I_all, scale)
+            if group is None:
+                r, c = be.lse_rows_cols(Ip, Tp, scale)      # both from one sweep over S
+            else:
+                r = be.lse(Ip, T_all, scale)
+                c = be.lse(Tp, I_all, scale)
             diag = be.row_dot(Ip, Tp)
             sdiag = be.sum(diag)
             parts[0] = be.sum(r) + be.sum(c) - (2.0 * scale) * sdiag

@@ -46,6 +46,10 @@ class FakeBackend:
     def lse(self, A, Ball, scale):
         return torch.logsumexp(scale * A @ Ball.t(), dim=1)
 
+    def lse_rows_cols(self, A, Bm, scale):
+        S = scale * A @ Bm.t()
+        return torch.logsumexp(S, dim=1), torch.logsumexp(S, dim=0)
+
     def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off, host_scale,
                     dev_scale, want_ws):
         G0 = A @ Ball.t()

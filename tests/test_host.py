@@ -65,7 +65,7 @@ def _check_tc_plans(pair):
         assert _plan(_lib.PATH_TC, nA, nB, D, 0) == (scb.choose_jparts(n_rb, 1, n_jb, 148), 2)
         jp, nsub = _plan(_lib.PATH_TC, nA, nB, D, 1)
         if pair and 4 < kch <= 8:      # gradient passes on CTA pairs: 74 pair-units, one item per row block and part
-            assert (jp, nsub) == (scb.choose_jparts(n_rb, 1, n_jb, 74), 4)
+            assert (jp, nsub) == (scb.choose_jparts(n_rb, 1, n_jb, 74, overhead=4.0), 4)
         else:
             assert (jp, nsub) == (scb.choose_jparts(n_rb, (kch + 3) // 4, n_jb, 148), 2)
 
