@@ -7,7 +7,7 @@ libscb200.so (hand-written CUDA: TMA + tcgen05/TMEM tile kernels); importing thi
 fails if that library cannot be loaded.
 """
 from . import _lib
-from .backend_cuda import choose_jparts, force_path, get_backend, set_fp32_mode
+from .backend_cuda import choose_jparts, force_path, get_backend, pair_span_plan, set_fp32_mode
 from .ladder import LOSS_TYPES, compose_loss, get_alpha, get_beta, ladder_weights, set_fused, weighted_loss
 from .losses import (centroid_alignment_loss, compute_centroids, compute_centroids_only, contrastive_loss,
                      contrastive_loss_roberta, fused_terms_loss, l2_normalize, lalign_loss, lunif_loss, normalized_centroids, operand_dtype, centroid_operand_dtype,

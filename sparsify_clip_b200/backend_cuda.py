@@ -50,6 +50,18 @@ def choose_jparts(n_rb, nsplit, n_jb, n_sm=148, max_parts=16, overhead=1.0):
     return best
 
 
+def pair_span_plan(n_rb, n_jb, n_sm=148):
+    """Host mirror of the CTA-pair kernel's work split (csrc/tc_pair.cu: scb_pair_span_plan): the linearised
+    (row block, column tile) space is cut into equal contiguous spans, one per CTA pair.
+    -> (pairs, tiles per pair, partial slots = largest number of segments a row block is cut into)."""
+    total = n_rb * n_jb
+    pairs = max(1, min(n_sm // 2, total))
+    span = max(1, -(-total // pairs), (n_jb + 14) // 15)      # at most 16 partial slots per row block
+    pairs = max(1, -(-total // span))
+    pmax = max(((rb + 1) * n_jb - 1) // span - (rb * n_jb) // span + 1 for rb in range(n_rb)) if n_rb else 1
+    return pairs, span, pmax
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 

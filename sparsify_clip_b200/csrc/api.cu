@@ -19,6 +19,7 @@ int scb_tc_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64
 int scb_tc_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
 int scb_tc_set_flags(int);
 bool scb_tc_use_pair(int D, int grad);
+void scb_pair_span_plan(int64_t n_rb, int64_t n_jb, int n_sm, int* n_pairs, int64_t* span, int* pmax);
 
 #define SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path)                                           \
   SCB_CHECK_ARG(scb_dtype_ok(dtype), SCB_E_DTYPE, "%s: unsupported dtype %d", __func__, (int)(dtype));             \
@@ -50,8 +51,10 @@ extern "C" int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, 
   if (path == SCB_PATH_TC) {
     const int kch = (D + 63) / 64;
     const int64_t n_rb = (nA + 127) / 128, n_jb = (nB + 127) / 128;
-    if (scb_tc_use_pair(D, grad) && n_sm >= 2) {       // one work item per CTA pair, no column groups
-      *jparts = scb_choose_jparts(n_rb, 1, n_jb, n_sm / 2, 4.0);
+    if (scb_tc_use_pair(D, grad) && n_sm >= 2) {       // equal contiguous spans of (row block, tile) per CTA pair
+      int np = 0;
+      int64_t span = 0;
+      scb_pair_span_plan(n_rb, n_jb, n_sm, &np, &span, jparts);
       *nsub = 4;
     } else {
       *jparts = scb_choose_jparts(n_rb, grad ? (kch + 3) / 4 : 1, n_jb, n_sm);

@@ -44,6 +44,7 @@ constexpr uint32_t kColOut = 0, kColS0 = 256;
 struct PairParams {
   int64_t nA, nB;
   int D, kch, n_rb, n_jb, jparts, nslots, fmt;
+  int64_t span;                // tiles of the linearised (row block, column tile) space per CTA pair
   float p0;
   const float* rowvec;
   const float* colvec;
@@ -180,7 +181,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t crank = cluster_ctarank();          // 0 / 1: which half of the output columns this CTA owns
   const uint32_t peer = crank ^ 1u;
   const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-  const int n_items = P.n_rb * P.jparts;
+  const int64_t total_tiles = (int64_t)P.n_rb * P.n_jb;
   const int gch = min(4, kch - 4 * (int)crank);      // 64-wide output chunks of my half
   const int gch_even = (gch + 1) & ~1;
 
@@ -210,14 +211,21 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_slot;
 
-  // item -> (row block, column part, tile range); `flip` alternates which CTA owns the even tiles
+  // Work distribution: the (row block, column tile) space is linearised row-block-major and cut into equal contiguous
+  // spans, one per CTA pair ("stream-K" over the column sweep): perfect balance for any shard size, and one pipeline
+  // fill/drain per row block a pair touches instead of one per (row block, part) item.  A span decomposes into
+  // segments (row block, tile range); a segment's output partial index `jp` is its ordinal inside its row block.
+  // `item_cnt` alternates which CTA of the pair owns the even tiles.
+#define SCB_PAIR_FOR_SEGMENTS()                                                                               \
+  for (int64_t g = (int64_t)pair_id * P.span, g_end = (g + P.span < total_tiles ? g + P.span : total_tiles); g < g_end; ++item_cnt)
 #define SCB_PAIR_ITEM_SETUP()                                                                              \
-  const int rb = item % P.n_rb;                                                                            \
-  const int jp = item / P.n_rb;                                                                            \
-  const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts); \
-  const int nt = jb_hi - jb_lo;                                                                            \
+  const int rb = (int)(g / P.n_jb);                                                                        \
+  const int jb_lo = (int)(g - (int64_t)rb * P.n_jb);                                                       \
+  const int nt = (int)(((int64_t)(P.n_jb - jb_lo) < g_end - g) ? (int64_t)(P.n_jb - jb_lo) : g_end - g);   \
+  const int jp = pair_id - (int)(((int64_t)rb * P.n_jb) / P.span);                                         \
   const int t_first = (int)((crank ^ (item_cnt & 1u)) & 1u);  /* my own tiles: t_first, t_first + 2, ... */ \
   const int n_own = (nt > t_first) ? (nt - t_first + 1) / 2 : 0;                                           \
+  g += nt;                                                                                                 \
   (void)rb; (void)jp; (void)jb_lo; (void)n_own
 
   // (setmaxnreg sits at the top of each role branch so that the role's code is dominated by it: ptxas only
@@ -229,7 +237,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) { tr.rec(0, (uint32_t)(ptx::globaltimer_ns() & 0xffffffffu)); tr.rec(0, (uint32_t)(ptx::globaltimer_ns() >> 32)); }
     Ring ring{0u, 0xFFFFFFFFu};
     uint32_t a_empty_par = 1, item_cnt = 0;
-    for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
+    SCB_PAIR_FOR_SEGMENTS() {
       SCB_PAIR_ITEM_SETUP();
       if (n_own > 0) {
         ptx::mbar_wait(bar(BAR_A_EMPTY), a_empty_par, 100);
@@ -285,7 +293,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t ring_lo0 = ptx::desc_lo(sm_ring, 16);
     const uint32_t ring_v_lo0 = ptx::desc_lo(sm_ring, kSlotBytes);   // MN-major V: 64-wide blocks one chunk apart
     constexpr uint32_t kChunkLo = kSlotBytes >> 4;
-    for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
+    SCB_PAIR_FOR_SEGMENTS() {
       SCB_PAIR_ITEM_SETUP();
       if (n_own > 0) {
         ptx::mbar_wait(bar(BAR_A_FULL), a_full_par, 200);
@@ -420,7 +428,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
     uint32_t ke = 0, item_cnt = 0;
     Tracer tr; tr.init(e == 0 ? P.trace : nullptr, pair_id, crank, 2);
-    for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
+    SCB_PAIR_FOR_SEGMENTS() {
       SCB_PAIR_ITEM_SETUP();
       const int64_t gi = (int64_t)rb * 128 + rrow;
       const bool row_ok = gi < P.nA;
@@ -544,6 +552,21 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
         if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
       }
+      // A row block is covered by 1 .. jparts segments; the consumers sum all `jparts` partial slots, so the segment
+      // that finishes the row block clears the slots nobody writes.
+      if (row_ok && jb_lo + nt == P.n_jb) {
+        const int ncol_half = 32 * gch;
+        for (int sl = jp + 1; sl < P.jparts; ++sl) {
+          float* orow = P.out + ((int64_t)sl * P.nA + gi) * P.D + 256 * (int)crank + h * ncol_half;
+          for (int c = 0; c < ncol_half; c += 4) {
+            if (256 * (int)crank + h * ncol_half + c + 4 <= P.D) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (int cc2 = 0; cc2 < 4; ++cc2) if (256 * (int)crank + h * ncol_half + c + cc2 < P.D) orow[c + cc2] = 0.f;
+          }
+          const int64_t o = ((int64_t)sl * 4 + 2 * (int)crank + h) * P.nA + gi;
+          if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = 0.f;
+          if (MODE == M_LUNIF_GRAD) { P.s0[o] = 0.f; P.s1[o] = 0.f; }
+        }
+      }
     }  // items
   }
   // =========================================================================== W senders
@@ -556,7 +579,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t peer_w_full = mapa(bar(BAR_W_FULL), peer);
     uint32_t kx = 0, item_cnt = 0;
     Tracer tr; tr.init(q == 0 ? P.trace : nullptr, pair_id, crank, 3);
-    for (int item = pair_id; item < n_items; item += n_pairs, ++item_cnt) {
+    SCB_PAIR_FOR_SEGMENTS() {
       SCB_PAIR_ITEM_SETUP();
       for (int t = t_first; t < nt; t += 2, ++kx) {
         const uint32_t b = kx & 1u;
@@ -601,6 +624,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   }
 #undef SCB_PAIR_ITEM_SETUP
+#undef SCB_PAIR_FOR_SEGMENTS
 
   // =========================================================================== teardown
   // nobody leaves while the peer may still write into this CTA's shared memory or signal its barriers
@@ -622,6 +646,31 @@ namespace {
 unsigned long long* g_pair_trace = nullptr;
 int g_pair_dbg = 0;
 
+}  // namespace
+
+// Span plan shared with the planner (scb_pass_plan): pairs used, tiles per pair, and the largest number of segments
+// any row block is cut into (= the number of output partial slots the caller must provide, "jparts").
+void scb_pair_span_plan(int64_t n_rb, int64_t n_jb, int n_sm, int* n_pairs, int64_t* span, int* pmax) {
+  const int64_t total = n_rb * n_jb;
+  int64_t np = n_sm / 2;
+  if (np > total) np = total;
+  if (np < 1) np = 1;
+  int64_t sp = (total + np - 1) / np;
+  if (sp < (n_jb + 14) / 15) sp = (n_jb + 14) / 15;      // at most 16 partial slots per row block
+  if (sp < 1) sp = 1;
+  np = (total + sp - 1) / sp;
+  int mx = 1;
+  for (int64_t rb = 0; rb < n_rb; ++rb) {
+    const int64_t first = (rb * n_jb) / sp, last = ((rb + 1) * n_jb - 1) / sp;
+    if ((int)(last - first + 1) > mx) mx = (int)(last - first + 1);
+  }
+  *n_pairs = (int)(np < 1 ? 1 : np);
+  *span = sp;
+  *pmax = mx;
+}
+
+namespace {
+
 template <int MODE>
 int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                 PairParams P, cudaStream_t s) {
@@ -633,7 +682,7 @@ int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
   P.n_rb = (int)((nA + 127) / 128);
   P.n_jb = (int)((nB + 127) / 128);
   SCB_CHECK_ARG(P.kch > 4 && P.kch <= 8, SCB_E_SHAPE, "pair kernel needs 256 < D <= 512 (D=%d)", D);
-  SCB_CHECK_ARG(P.jparts >= 1 && P.jparts <= P.n_jb, SCB_E_ARG, "jparts=%d outside [1, %d]", P.jparts, P.n_jb);
+
   P.fmt = (dtype == SCB_BF16) ? 1 : 0;
   const int budget = 232448 - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
   const int n_astat = P.kch < kAStat ? P.kch : kAStat;
@@ -663,9 +712,10 @@ int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
     if (e != cudaSuccess) { scb_set_error("cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  const int n_items = P.n_rb * P.jparts;
-  const int max_pairs = num_sms / 2;
-  const int n_pairs = n_items < max_pairs ? n_items : max_pairs;
+  int n_pairs = 1, pmax = 1;
+  scb_pair_span_plan(P.n_rb, P.n_jb, num_sms, &n_pairs, &P.span, &pmax);
+  SCB_CHECK_ARG(P.jparts == pmax, SCB_E_ARG, "pair kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
+                P.jparts, pmax);
   if (P.kch == 8) k_tc_pair<MODE, 8><<<2 * n_pairs, kThreads, smem, s>>>(tmA, tmB, P);
   else k_tc_pair<MODE, 0><<<2 * n_pairs, kThreads, smem, s>>>(tmA, tmB, P);
   SCB_CHECK_LAUNCH("tc_pair");

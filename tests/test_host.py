@@ -64,8 +64,8 @@ def _check_tc_plans(pair):
         n_rb, n_jb, kch = (nA + 127) // 128, (nB + 127) // 128, (D + 63) // 64
         assert _plan(_lib.PATH_TC, nA, nB, D, 0) == (scb.choose_jparts(n_rb, 1, n_jb, 148), 2)
         jp, nsub = _plan(_lib.PATH_TC, nA, nB, D, 1)
-        if pair and 4 < kch <= 8:      # gradient passes on CTA pairs: 74 pair-units, one item per row block and part
-            assert (jp, nsub) == (scb.choose_jparts(n_rb, 1, n_jb, 74, overhead=4.0), 4)
+        if pair and 4 < kch <= 8:      # gradient passes on CTA pairs: equal contiguous tile spans per pair
+            assert (jp, nsub) == (scb.pair_span_plan(n_rb, n_jb, 148)[2], 4)
         else:
             assert (jp, nsub) == (scb.choose_jparts(n_rb, (kch + 3) // 4, n_jb, 148), 2)
 
