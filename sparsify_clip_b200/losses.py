@@ -213,7 +213,7 @@ class _FusedTermsFn(torch.autograd.Function):
             if w_a != 0.0 or w_t != 0.0:
                 T_all, h = _all_gather_rows_async(Tp, group)
                 pending.append(h)
-        # scalar partial sums of this rank; ONE all-reduce for all of them at the end
+        # scalar partial sums of this rank
         #   0: anchor (sum r + sum c - 2/tau sum diag)   1: L_align   2, 3: L_unif row sums (I, T)   4: d/dtau
         parts = torch.zeros(5, dtype=torch.float32, device=dev)
         if w_l != 0.0:
@@ -222,7 +222,8 @@ class _FusedTermsFn(torch.autograd.Function):
             h.wait()
         an_I = an_T = None
         scale = 0.0
-        rc_pending = None
+        r = c = None
+        # every B x B sweep that does not need the other ranks' statistics first: LSE and L_unif
         if w_a != 0.0:
             tau = float(tau_t) if tau_t is not None else float(tau_f)
             scale = 1.0 / tau
@@ -234,12 +235,6 @@ class _FusedTermsFn(torch.autograd.Function):
             diag = be.row_dot(Ip, Tp)
             sdiag = be.sum(diag)
             parts[0] = be.sum(r) + be.sum(c) - (2.0 * scale) * sdiag
-            r_all, c_all = r, c
-            if group is not None and (need or need_tau):
-                # exchange step 2: both LSE vectors in one gather, overlapped with the L_unif sweeps below
-                rc = torch.stack((r, c)).contiguous()
-                rc_all = torch.empty((ws, 2, n), dtype=torch.float32, device=dev)
-                rc_pending = (dist.all_gather_into_tensor(rc_all, rc, group=group, async_op=True), rc_all)
         un_I = un_T = None
         cores = {}
         for (wu, Xp, X_all, needx, which, slot) in ((w_i, Ip, I_all, need_I, "I", 2), (w_t, Tp, T_all, need_T, "T", 3)):
@@ -248,11 +243,20 @@ class _FusedTermsFn(torch.autograd.Function):
             core = be.lunif_core(Xp, X_all, float(t_unif), off, needx)
             parts[slot] = core["rs_sum"]
             cores[which] = (core, wu, needx)
+        # ---- exchange step 2: ONE small gather carries r, c and the scalar partials of every rank.  It is issued
+        # between sweeps, not under one: an NCCL kernel that shares the SMs with a persistent sweep slows the sweep
+        # more than the overlap saves (measured at 8 GPUs).
+        r_all, c_all = r, c
+        gathered = False
+        if group is not None and w_a != 0.0 and (need or need_tau):
+            pack = torch.cat((r, c, parts[:4]))
+            pack_all = torch.empty((ws, 2 * n + 4), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(pack_all, pack, group=group)
+            r_all = pack_all[:, :n].reshape(-1)
+            c_all = pack_all[:, n:2 * n].reshape(-1)
+            parts = torch.cat((pack_all[:, 2 * n:].sum(0), parts[4:]))
+            gathered = True
         if w_a != 0.0 and (need or need_tau):
-            if rc_pending is not None:
-                rc_pending[0].wait()
-                r_all = rc_pending[1][:, 0, :].reshape(-1)
-                c_all = rc_pending[1][:, 1, :].reshape(-1)
             coef = w_a * scale / (2.0 * B)
             if need_I or need_tau:
                 p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
@@ -262,8 +266,12 @@ class _FusedTermsFn(torch.autograd.Function):
             if need_T:
                 p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
                 an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
-        # ---- exchange step 3: every scalar in one all-reduce
-        _all_reduce_(parts, group)
+        # ---- exchange step 3 (only what step 2 did not carry): d/dtau, or everything when there is no anchor term
+        if group is not None:
+            if not gathered:
+                _all_reduce_(parts, group)
+            elif need_tau:
+                _all_reduce_(parts[4:], group)
         loss = (w_a / (2.0 * B)) * parts[0] + (w_l / B) * parts[1]
         for which, (core, wu, needx) in cores.items():
             ssum = parts[2 if which == "I" else 3] * 0.5
