@@ -121,6 +121,10 @@ int scb_lse2_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, 
                   float scale, int jparts, float* part_m, float* part_l, float* col_ref, float* col_sum, void* stream);
 /* lse[j] = natural-log column LSE from the nparts = 4*ceil(nA/128) strip partials. */
 int scb_colstat_combine(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* lse, void* stream);
+/* the same fold kept as a pair: sum over the partials = sum_out[j] * 2^ref_out[j] (log2 domain).  Row-sharded runs
+ * all-gather these pairs (each rank sweeps its rows against all columns) and fold them once more. */
+int scb_colstat_partial(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* ref_out, float* sum_out,
+                        void* stream);
 /* *flag = (2 * scale * log2(e) * max_i |A_i| * max_j |B_j| >= 90) from the squared row norms (scb_row_sqnorm). */
 int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* sqnB, int64_t nB, float scale, int* flag, void* stream);
 /* scb_lse_pass / scb_lse_combine that do nothing unless *run_flag != 0 (device pointer). */

@@ -34,6 +34,7 @@ SIGNATURES = {
     "scb_lse_combine": [_vp, _vp, _i32, _i64, _vp, _vp],
     "scb_lse2_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "scb_colstat_combine": [_vp, _vp, _i32, _i64, _vp, _vp],
+    "scb_colstat_partial": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
     "scb_lse2_spread_flag": [_vp, _i64, _vp, _i64, _f32, _vp, _vp],
     "scb_lse_pass_cond": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp],
     "scb_lse_combine_cond": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],

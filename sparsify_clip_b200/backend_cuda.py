@@ -276,6 +276,49 @@ class CudaBackend:
         self._count(6)
         return r, c
 
+    def lse_rows_colparts(self, A, Bm_all, Bm_rows, A_all, scale):
+        """Row-sharded variant of lse_rows_cols.  A = my rows, Bm_all = all columns, Bm_rows = my rows of the column
+        side, A_all = all rows.  Returns None off the tensor-core path, else
+        (r [nA], M [nB], L [nB], c_exact_rows [nA], flag): column partial over MY rows = L * 2^M (log2 domain);
+        c_exact_rows / flag = the conditional exact sweep (valid where flag != 0; flag is a global norm bound, the
+        same on every rank)."""
+        nA, D = A.shape
+        nB = Bm_all.shape[0]
+        path = self.path_for(A, Bm_all)
+        if path != PATH_TC:
+            return None
+        dev = A.device
+        jp, _ = self._plan(path, nA, nB, D, False, dev)
+        jp2, nsub2 = self._plan(path, Bm_rows.shape[0], A_all.shape[0], D, False, dev)
+        n_strips = 4 * ((nA + 127) // 128)
+        f32 = dict(dtype=torch.float32, device=dev)
+        nsub = 4
+        pm, pl = torch.empty(jp * nsub, nA, **f32), torch.empty(jp * nsub, nA, **f32)
+        cref, csum = torch.empty(n_strips, (nB + 31) // 32, **f32), torch.empty(n_strips, nB, **f32)
+        r, M, L = torch.empty(nA, **f32), torch.empty(nB, **f32), torch.empty(nB, **f32)
+        nR = Bm_rows.shape[0]
+        c_exact = torch.zeros(nR, **f32)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        pm2, pl2 = torch.empty(jp2 * nsub2, nR, **f32), torch.empty(jp2 * nsub2, nR, **f32)
+        sqa, sqb = self.row_sqnorm(A_all), self.row_sqnorm(Bm_all)
+        st = self._stream()
+        with torch.cuda.device(dev):
+            check(self.lib.scb_lse2_spread_flag(_ptr(sqa), A_all.shape[0], _ptr(sqb), nB, float(scale), _ptr(flag), st),
+                  "lse2_spread_flag")
+            with self._Timed(self, "lse"):
+                check(self.lib.scb_lse2_pass(_ptr(A), nA, _ptr(Bm_all), nB, D, A.stride(0), Bm_all.stride(0), _DT[A.dtype],
+                                             float(scale), jp, _ptr(pm), _ptr(pl), _ptr(cref), _ptr(csum), st), "lse2_pass")
+            check(self.lib.scb_lse_combine(_ptr(pm), _ptr(pl), jp * nsub, nA, _ptr(r), st), "lse_combine")
+            check(self.lib.scb_colstat_partial(_ptr(cref), _ptr(csum), n_strips, nB, _ptr(M), _ptr(L), st), "colstat_partial")
+            with self._Timed(self, "lse"):
+                check(self.lib.scb_lse_pass_cond(_ptr(Bm_rows), nR, _ptr(A_all), A_all.shape[0], D, Bm_rows.stride(0),
+                                                 A_all.stride(0), _DT[A.dtype], float(scale), jp2, _ptr(pm2), _ptr(pl2),
+                                                 _ptr(flag), st), "lse_pass_cond")
+            check(self.lib.scb_lse_combine_cond(_ptr(pm2), _ptr(pl2), jp2 * nsub2, nR, _ptr(c_exact), _ptr(flag), st),
+                  "lse_combine_cond")
+        self._count(6)
+        return r, M, L, c_exact, flag
+
     def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off,
                     host_scale, dev_scale, want_ws):
         """dA = s * [ sum_j (P_ij + Q_ij) Ball_j  (j != diagonal)  +  (P_ii + Q_ii - 2) V_i ]  (fp32 [nA, D]);

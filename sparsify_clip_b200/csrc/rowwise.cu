@@ -250,6 +250,26 @@ __global__ void __launch_bounds__(256) k_colstat_combine(const float* __restrict
   lse[j] = (M + log2f(L)) * SCB_LN2;
 }
 
+// same fold, but the result stays a (reference, sum) pair in the log2 domain: the sharded path folds the pairs of all
+// ranks after one all-gather
+__global__ void __launch_bounds__(256) k_colstat_partial(const float* __restrict__ cref, const float* __restrict__ csum,
+                                                         int nparts, int64_t n, float* __restrict__ Mout,
+                                                         float* __restrict__ Lout) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n) return;
+  const int64_t nref = (n + 31) / 32;
+  float M = -INFINITY, L = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    const float r = __ldg(cref + (int64_t)p * nref + (j >> 5));
+    const float v = __ldcs(csum + (int64_t)p * n + j);
+    if (r == -INFINITY || v == 0.f) continue;
+    if (r > M) { L *= exp2f(M - r); M = r; }
+    L += v * exp2f(r - M);
+  }
+  Mout[j] = M;
+  Lout[j] = L;
+}
+
 // flag = 1 when the logits can spread by more than `bound` (log2 units) inside one block of the fused pass:
 // 2 * scale * log2e * max_i |a_i| * max_j |b_j| >= bound   (sqn = squared row norms)
 __global__ void __launch_bounds__(1024) k_spread_flag(const float* __restrict__ sqnA, int64_t nA, const float* __restrict__ sqnB,
@@ -621,5 +641,14 @@ extern "C" int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* 
   SCB_CHECK_ARG(sqnA && sqnB && flag && nA >= 0 && nB >= 0 && scale > 0.f, SCB_E_ARG, "lse2_spread_flag: bad argument");
   k_spread_flag<<<1, 1024, 0, (cudaStream_t)stream>>>(sqnA, nA, sqnB, nB, scale, 90.f, flag);
   SCB_CHECK_LAUNCH("lse2_spread_flag");
+  return 0;
+}
+
+extern "C" int scb_colstat_partial(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* ref_out,
+                                   float* sum_out, void* stream) {
+  SCB_CHECK_ARG(col_ref && col_sum && ref_out && sum_out && nparts > 0 && n >= 0, SCB_E_ARG, "colstat_partial: bad argument");
+  if (n == 0) return 0;
+  k_colstat_partial<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, ref_out, sum_out);
+  SCB_CHECK_LAUNCH("colstat_partial");
   return 0;
 }

@@ -227,14 +227,21 @@ class _FusedTermsFn(torch.autograd.Function):
         if w_a != 0.0:
             tau = float(tau_t) if tau_t is not None else float(tau_f)
             scale = 1.0 / tau
+            colparts = None
             if group is None:
                 r, c = be.lse_rows_cols(Ip, Tp, scale)      # both from one sweep over S
             else:
-                r = be.lse(Ip, T_all, scale)
-                c = be.lse(Tp, I_all, scale)
+                colparts = be.lse_rows_colparts(Ip, T_all, Tp, I_all, scale)
+                if colparts is None:                        # not on the tensor-core path: two sweeps
+                    r = be.lse(Ip, T_all, scale)
+                    c = be.lse(Tp, I_all, scale)
+                else:                                       # one sweep: my rows of S; the column sums are folded
+                    r = colparts[0]                         # over the ranks after the gather below
             diag = be.row_dot(Ip, Tp)
             sdiag = be.sum(diag)
-            parts[0] = be.sum(r) + be.sum(c) - (2.0 * scale) * sdiag
+            parts[0] = be.sum(r) - (2.0 * scale) * sdiag
+            if colparts is None:
+                parts[0] = parts[0] + be.sum(c)
         un_I = un_T = None
         cores = {}
         for (wu, Xp, X_all, needx, which, slot) in ((w_i, Ip, I_all, need_I, "I", 2), (w_t, Tp, T_all, need_T, "T", 3)):
@@ -248,13 +255,26 @@ class _FusedTermsFn(torch.autograd.Function):
         # more than the overlap saves (measured at 8 GPUs).
         r_all, c_all = r, c
         gathered = False
-        if group is not None and w_a != 0.0 and (need or need_tau):
-            pack = torch.cat((r, c, parts[:4]))
-            pack_all = torch.empty((ws, 2 * n + 4), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(pack_all, pack, group=group)
+        if group is not None and w_a != 0.0 and (need or need_tau or colparts is not None):
+            if colparts is None:
+                pieces = (r, c, parts[:4])
+            else:
+                _, cM, cL, c_exact, flag = colparts
+                pieces = (r, c_exact, parts[:4], cM, cL)
+            pack = torch.cat([x.to(torch.float32) for x in pieces])
+            pack_flat = torch.empty(ws * pack.numel(), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(pack_flat, pack, group=group)
+            pack_all = pack_flat.view(ws, -1)
             r_all = pack_all[:, :n].reshape(-1)
             c_all = pack_all[:, n:2 * n].reshape(-1)
-            parts = torch.cat((pack_all[:, 2 * n:].sum(0), parts[4:]))
+            parts = torch.cat((pack_all[:, 2 * n:2 * n + 4].sum(0), parts[4:]))
+            if colparts is not None:
+                Mr, Lr = pack_all[:, 2 * n + 4:2 * n + 4 + B], pack_all[:, 2 * n + 4 + B:]
+                Mx = Mr.max(0).values
+                c_fused = (Mx + torch.log2((Lr * torch.exp2(Mr - Mx)).sum(0))) * math.log(2.0)
+                c_all = torch.where(flag != 0, c_all, c_fused)          # exact second sweep where the bound demanded it
+                c = c_all[off:off + n].contiguous()
+                parts[0] = parts[0] + c_all.sum()
             gathered = True
         if w_a != 0.0 and (need or need_tau):
             coef = w_a * scale / (2.0 * B)

@@ -50,6 +50,13 @@ class FakeBackend:
         S = scale * A @ Bm.t()
         return torch.logsumexp(S, dim=1), torch.logsumexp(S, dim=0)
 
+    def lse_rows_colparts(self, A, Bm_all, Bm_rows, A_all, scale):
+        S = (scale * A @ Bm_all.t()) / 0.6931471805599453        # log2 domain, as the kernels
+        M = S.max(0).values
+        L = torch.exp2(S - M).sum(0)
+        r = torch.logsumexp(scale * A @ Bm_all.t(), dim=1)
+        return r, M, L, torch.zeros(Bm_rows.shape[0], dtype=A.dtype), torch.zeros(1, dtype=torch.int32)
+
     def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off, host_scale,
                     dev_scale, want_ws):
         G0 = A @ Ball.t()

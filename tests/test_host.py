@@ -149,7 +149,7 @@ def test_uniformity_signatures_run():
 
 
 # ----------------------------------------------------------------------------- sharded algebra (gloo, 2 ranks)
-def _worker(rank, world, port, I, T, tau, out):
+def _worker(rank, world, port, I, T, tau, out, cen=0.7):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     backend_cuda.set_backend(FakeBackend())
@@ -157,11 +157,32 @@ def _worker(rank, world, port, I, T, tau, out):
     Il = I[rank * n:(rank + 1) * n].clone().requires_grad_(True)
     Tl = T[rank * n:(rank + 1) * n].clone().requires_grad_(True)
     tp = torch.nn.Parameter(torch.tensor(tau, dtype=torch.float64))
-    w = dict(anchor=1.0, align=1.5, unif_img=0.5, unif_txt=0.25, unif_cen=0.7)
+    w = dict(anchor=1.0, align=1.5, unif_img=0.5, unif_txt=0.25, unif_cen=cen)
     loss = scb.weighted_loss(Il, Tl, tp, w, group=True)
     (loss * 2.0).backward()
     out[rank] = (loss.item(), Il.grad.numpy() / 2.0, Tl.grad.numpy() / 2.0, tp.grad.item() / 2.0)
     dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_fused_composition_two_ranks():
+    """Centroid-free weights take the fused autograd node: one-sweep LSE with the column sums folded over the ranks,
+    the packed (r, c, scalars, column partials) gather and scb_grad_combine, all against the full-batch oracle."""
+    g = torch.Generator().manual_seed(11)
+    B, D, tau = 24, 16, 0.2
+    I = torch.nn.functional.normalize(torch.randn(B, D, generator=g, dtype=torch.float64), dim=-1)
+    T = torch.nn.functional.normalize(I + 0.5 * torch.randn(B, D, generator=g, dtype=torch.float64), dim=-1)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, 30517 + os.getpid() % 1000, I, T, tau, out, 0.0), nprocs=2, join=True)
+    ref_loss, dI, dT, dtau, _ = cf.weighted_loss(I.numpy(), T.numpy(), tau, 1.0, 1.5, 0.5, 0.25, 0.0)
+    n = B // 2
+    for r in (0, 1):
+        loss, gI, gT, gtau = out[r]
+        assert loss == pytest.approx(ref_loss, rel=1e-6)         # scalars travel as fp32 in the packed gather
+        assert np.abs(gI - dI[r * n:(r + 1) * n]).max() < 1e-6
+        assert np.abs(gT - dT[r * n:(r + 1) * n]).max() < 1e-6
+        assert gtau == pytest.approx(dtau, rel=1e-5)
 
 
 @pytest.mark.timeout(120)
