@@ -233,41 +233,46 @@ __global__ void __launch_bounds__(256) k_lse_combine_cond(const float* __restric
   lse[i] = (M + log2f(L)) * SCB_LN2;
 }
 
-// column LSE from the per-strip partials of the fused pass: lse[j] = ln sum_p csum[p][j] 2^{cref[p][j/32]}
-__global__ void __launch_bounds__(256) k_colstat_combine(const float* __restrict__ cref, const float* __restrict__ csum,
-                                                         int nparts, int64_t n, float* __restrict__ lse) {
-  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (j >= n) return;
+// Fold of the per-strip column partials of the fused pass: sum_p csum[p][j] 2^{cref[p][j/32]}.
+// A block owns 32 columns; its 8 warps split the partials (warp w takes p = w, w+8, ...: every load is one coalesced
+// 128-byte row of csum), then the 8 (reference, sum) pairs per column meet in shared memory.  With one thread per column
+// walking all 4*n_rb partials the fold was latency-bound: 325 us at c3 for 134 MB (now HBM-bound).
+// FINAL: write the natural-log column LSE; else keep the (reference, sum) pair in the log2 domain.
+template <bool FINAL>
+__global__ void __launch_bounds__(256) k_colstat_fold(const float* __restrict__ cref, const float* __restrict__ csum, int nparts,
+                                                      int64_t n, float* __restrict__ out0, float* __restrict__ out1) {
+  __shared__ float shM[8][32], shL[8][32];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * 32 + lane;
   const int64_t nref = (n + 31) / 32;
   float M = -INFINITY, L = 0.f;
-  for (int p = 0; p < nparts; ++p) {          // online: one pass over the partials (coalesced across threads)
-    const float r = __ldg(cref + (int64_t)p * nref + (j >> 5));
-    const float v = __ldcs(csum + (int64_t)p * n + j);
-    if (r == -INFINITY || v == 0.f) continue;
-    if (r > M) { L *= exp2f(M - r); M = r; }
-    L += v * exp2f(r - M);
+  if (j < n) {
+    for (int p = w; p < nparts; p += 8) {
+      const float r = __ldg(cref + (int64_t)p * nref + blockIdx.x);
+      const float v = __ldcs(csum + (int64_t)p * n + j);
+      if (r == -INFINITY || v == 0.f) continue;
+      if (r > M) { L *= exp2f(M - r); M = r; }
+      L += v * exp2f(r - M);
+    }
   }
-  lse[j] = (M + log2f(L)) * SCB_LN2;
-}
-
-// same fold, but the result stays a (reference, sum) pair in the log2 domain: the sharded path folds the pairs of all
-// ranks after one all-gather
-__global__ void __launch_bounds__(256) k_colstat_partial(const float* __restrict__ cref, const float* __restrict__ csum,
-                                                         int nparts, int64_t n, float* __restrict__ Mout,
-                                                         float* __restrict__ Lout) {
-  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (j >= n) return;
-  const int64_t nref = (n + 31) / 32;
-  float M = -INFINITY, L = 0.f;
-  for (int p = 0; p < nparts; ++p) {
-    const float r = __ldg(cref + (int64_t)p * nref + (j >> 5));
-    const float v = __ldcs(csum + (int64_t)p * n + j);
-    if (r == -INFINITY || v == 0.f) continue;
-    if (r > M) { L *= exp2f(M - r); M = r; }
-    L += v * exp2f(r - M);
+  shM[w][lane] = M;
+  shL[w][lane] = L;
+  __syncthreads();
+  if (w == 0 && j < n) {
+    float Mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) Mx = fmaxf(Mx, shM[k][lane]);
+    float Ls = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (shM[k][lane] != -INFINITY) Ls += shL[k][lane] * exp2f(shM[k][lane] - Mx);
+    if (FINAL) {
+      out0[j] = (Mx + log2f(Ls)) * SCB_LN2;
+    } else {
+      out0[j] = Mx;
+      out1[j] = Ls;
+    }
   }
-  Mout[j] = M;
-  Lout[j] = L;
 }
 
 // flag = 1 when the logits can spread by more than `bound` (log2 units) inside one block of the fused pass:
@@ -631,7 +636,7 @@ extern "C" int scb_lse_combine_cond(const float* part_m, const float* part_l, in
 extern "C" int scb_colstat_combine(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* lse, void* stream) {
   SCB_CHECK_ARG(col_ref && col_sum && lse && nparts > 0 && n >= 0, SCB_E_ARG, "colstat_combine: bad argument");
   if (n == 0) return 0;
-  k_colstat_combine<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, lse);
+  k_colstat_fold<true><<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, lse, nullptr);
   SCB_CHECK_LAUNCH("colstat_combine");
   return 0;
 }
@@ -648,7 +653,7 @@ extern "C" int scb_colstat_partial(const float* col_ref, const float* col_sum, i
                                    float* sum_out, void* stream) {
   SCB_CHECK_ARG(col_ref && col_sum && ref_out && sum_out && nparts > 0 && n >= 0, SCB_E_ARG, "colstat_partial: bad argument");
   if (n == 0) return 0;
-  k_colstat_partial<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, ref_out, sum_out);
+  k_colstat_fold<false><<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, ref_out, sum_out);
   SCB_CHECK_LAUNCH("colstat_partial");
   return 0;
 }
