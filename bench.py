@@ -85,6 +85,9 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t_end = time.time() + 5.0          # NVML initialisation done = first sample delivered
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
