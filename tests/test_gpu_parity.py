@@ -234,7 +234,8 @@ def test_ladder_on_gpu_matches_oracle():
             assert np.linalg.norm(Ig.grad.double().cpu().numpy() - dI) <= 1e-5 * max(np.linalg.norm(dI), 1e-30), (lt, epoch)
 
 
-@pytest.mark.parametrize("B,D,dtype", [(384, 512, torch.bfloat16), (200, 128, torch.float32), (1000, 768, torch.float16)])
+@pytest.mark.parametrize("B,D,dtype", [(384, 512, torch.bfloat16), (200, 128, torch.float32), (1000, 768, torch.float16),
+                                       (150, 20, torch.float32), (131, 44, torch.bfloat16)])      # D % 8 != 0: scalar paths
 def test_fused_composition_equals_the_sum_of_its_terms(B, D, dtype):
     """weighted_loss through the fused autograd node (scb_grad_combine) vs the term-by-term composition: same passes,
     so the loss agrees to fp32 rounding and the gradients to the rounding of the output dtype."""
