@@ -325,31 +325,48 @@ def run_ours(args):
     # ---- end to end through the public API from pinned host memory
     hI = I0.to(torch.bfloat16).cpu().pin_memory()
     hT = T0.to(torch.bfloat16).cpu().pin_memory()
-    dI = torch.empty(n, D, dtype=torch.bfloat16, device=dev)
-    dT = torch.empty(n, D, dtype=torch.bfloat16, device=dev)
+    # Input pipeline: the H2D copy of step k+1 runs on a copy stream into the other of two device buffers while step k
+    # computes (what a training loop's prefetcher does); every step's copy, its compute and the D2H read of its loss lie
+    # inside one timed region that spans all steps, the first copy fully exposed.
+    dbuf = [(torch.empty(n, D, dtype=torch.bfloat16, device=dev), torch.empty(n, D, dtype=torch.bfloat16, device=dev))
+            for _ in range(2)]
     hloss = torch.empty((), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        dI.copy_(hI, non_blocking=True)
-        dT.copy_(hT, non_blocking=True)
-        Iv = dI.detach().requires_grad_(True)
-        Tv = dT.detach().requires_grad_(True)
-        l = step(Iv, Tv)
-        hloss.copy_(l.detach(), non_blocking=True)
+    def prefetch(k):
+        bsel = k & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[bsel])          # the step that last read this buffer has finished
+            dbuf[bsel][0].copy_(hI, non_blocking=True)
+            dbuf[bsel][1].copy_(hT, non_blocking=True)
+            ev_in[bsel].record(copy_stream)
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(ksteps):
+        cur = torch.cuda.current_stream()
+        for e in ev_free:
+            e.record(cur)
+        prefetch(0)
+        for k in range(ksteps):
+            if k + 1 < ksteps:
+                prefetch(k + 1)
+            cur.wait_event(ev_in[k & 1])
+            Iv = dbuf[k & 1][0].detach().requires_grad_(True)
+            Tv = dbuf[k & 1][1].detach().requires_grad_(True)
+            l = step(Iv, Tv)
+            ev_free[k & 1].record(cur)
+            hloss.copy_(l.detach(), non_blocking=True)
+
+    e2e_run(3)
     barrier()
-    e2e_ev = []
     ke = max(3, min(args.steps, 10))
-    for _ in range(ke):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_step()
-        e1.record()
-        e2e_ev.append((e0, e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(ke)
+    e1.record()
     barrier()
+    e2e_ev = [(e0, e1)]
     et = torch.tensor([sum(a.elapsed_time(b) for a, b in e2e_ev) / ke], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
@@ -367,7 +384,9 @@ def run_ours(args):
                        "launch": "one CUDA-graph replay per step" if graphed is not None else "eager launches"},
             "loss": loss_val,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * D * 2, "d2h_bytes_per_step": 4,
-                    "ms_per_step": et.item()},
+                    "ms_per_step": et.item(),
+                    "how": "public API on device buffers filled from pinned host memory; the copy of step k+1 overlaps "
+                           "the compute of step k (double buffer, copy stream); one CUDA-event region over all steps"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
