@@ -255,3 +255,132 @@ if __name__ == "__main__":
             print(f"{name:40s} DEADLOCK {busy}")
         else:
             print(f"{name:40s} {per:8.0f} cycles per 2 tiles   tensor busy {busy:.2f}")
+
+
+def simulate_order(order="A", nt=128, nslots=6, lag_own=2, lag_peer=3, L_tma=1500.0, tma_bw=80.0, E=2300.0, X=3200.0,
+                   ack=400.0, chunk_clk=330.0, v_pair_clk=600.0, kch=8, gch=4, issue_cost=40.0, a_stream=2):
+    """Like simulate() (single Wrecv, DSMEM hand-over) but the MMA/TMA issue order inside a step is a parameter:
+    ops of the step of own tile t: MMA1 chunks c0..c7 of t, MMA2 groups o0,o1 of own tile t-lag_own, p0,p1 of peer tile
+    t-lag_peer.  order: 'A' c0-7 o0 o1 p0 p1 (as built) | 'B' c0-3 o0 c4-7 o1 p0 p1 | 'C' c0-1 o0 c2-3 o1 c4-5 p0 c6-7 p1
+    | 'D' c0-3 o0 o1 c4-7 p0 p1."""
+    sim = Sim()
+    CH = 16384.0
+    for c in (0, 1):
+        for s in range(nslots):
+            sim.bar((c, "full", s), 1)
+            sim.bar((c, "empty", s), 1)
+        for b in (0, 1):
+            sim.bar((c, "s_full", b), 1)
+            sim.bar((c, "s_empty", b), 2)
+            sim.bar((c, "g_full", b), 1)
+        sim.bar((c, "w_full", 0), 1)
+        sim.bar((c, "w_empty", 0), 1)
+    pipe_free, pipe_busy, tma_free, end_time = [0.0, 0.0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0]
+    pat = {"A": "c0 c1 c2 c3 c4 c5 c6 c7 o0 o1 p0 p1", "B": "c0 c1 c2 c3 o0 c4 c5 c6 c7 o1 p0 p1",
+           "C": "c0 c1 o0 c2 c3 o1 c4 c5 p0 c6 c7 p1", "D": "c0 c1 c2 c3 o0 o1 c4 c5 c6 c7 p0 p1",
+           "E": "o0 c0 c1 c2 c3 o1 c4 c5 c6 c7 p0 p1"}[order].split()
+
+    def own(c, t):
+        return (t & 1) == c
+
+    def ops(c):
+        seq = []
+        for s in range(c, nt + max(lag_own, lag_peer) + 2, 2):
+            for o in pat:
+                if o[0] == "c":
+                    if s < nt:
+                        seq.append(("c", s, int(o[1])))
+                elif o[0] == "o":
+                    if 0 <= s - lag_own < nt:
+                        seq.append(("o", s - lag_own, int(o[1])))
+                else:
+                    if 0 <= s - lag_peer < nt:
+                        seq.append(("p", s - lag_peer, int(o[1])))
+        return seq
+
+    def nslots_of(op):
+        if op[0] == "c":
+            return 2 if op[2] >= kch - a_stream else 1
+        return 2
+
+    def producer(c):
+        t = yield ("delay", 0)
+        slot, uses = 0, defaultdict(int)
+        for op in ops(c):
+            for _ in range(nslots_of(op)):
+                t = yield ("wait", (c, "empty", slot), uses[slot] - 1)
+                uses[slot] += 1
+                start = max(t + L_tma, tma_free[c])
+                tma_free[c] = start + CH / tma_bw
+                t = yield ("arrive", (c, "full", slot), tma_free[c])
+                t = yield ("delay", 20)
+                slot = (slot + 1) % nslots
+
+    def mma(c):
+        t = yield ("delay", 0)
+        slot, uses = 0, defaultdict(int)
+        idx = {}            # own tile -> own index ; peer tile -> peer index
+        no = npeer = 0
+        for op in ops(c):
+            kind, tile, sub = op
+            if kind == "c":
+                k1 = tile // 2
+                if sub == 0:
+                    t = yield ("wait", (c, "s_empty", k1 & 1), (k1 >> 1) - 1)
+            elif kind == "o":
+                k2 = tile // 2
+                if sub == 0:
+                    t = yield ("wait", (c, "g_full", k2 & 1), k2 >> 1)
+            else:
+                kp = tile // 2
+                if sub == 0:
+                    t = yield ("wait", (c, "w_full", 0), kp)
+            used = []
+            for _ in range(nslots_of(op)):
+                t = yield ("wait", (c, "full", slot), uses[slot])
+                uses[slot] += 1
+                used.append(slot)
+                slot = (slot + 1) % nslots
+            t = yield ("delay", issue_cost)
+            start = max(t, pipe_free[c])
+            dur = chunk_clk if kind == "c" else v_pair_clk
+            pipe_free[c] = start + dur
+            pipe_busy[c] += dur
+            fin = pipe_free[c]
+            for u in used:
+                t = yield ("arrive", (c, "empty", u), fin + 30)
+            if kind == "c" and sub == kch - 1:
+                t = yield ("arrive", (c, "s_full", (tile // 2) & 1), fin + 30)
+            if kind == "o" and sub == 1:
+                t = yield ("arrive", (c, "s_empty", (tile // 2) & 1), fin + 30)
+            if kind == "p" and sub == 1:
+                t = yield ("arrive", (1 - c, "w_empty", 0), fin + 30 + ack)
+            end_time[c] = max(end_time[c], fin)
+
+    def epilogue(c):
+        t = yield ("delay", 0)
+        for k, tile in enumerate(range(c, nt, 2)):
+            t = yield ("wait", (c, "s_full", k & 1), k >> 1)
+            t = yield ("delay", E)
+            t = yield ("arrive", (c, "g_full", k & 1))
+
+    def sender(c):
+        t = yield ("delay", 0)
+        for k, tile in enumerate(range(c, nt, 2)):
+            t = yield ("wait", (c, "g_full", k & 1), k >> 1)
+            t = yield ("delay", 150)
+            t = yield ("arrive", (c, "s_empty", k & 1))
+            t = yield ("wait", (c, "w_empty", 0), k - 1)
+            t = yield ("delay", X)
+            t = yield ("arrive", (1 - c, "w_full", 0))
+
+    for c in (0, 1):
+        sim.add_role((c, "tma"), producer(c))
+        sim.add_role((c, "mma"), mma(c))
+        sim.add_role((c, "epi"), epilogue(c))
+        sim.add_role((c, "snd"), sender(c))
+    stuck = sim.run()
+    if stuck:
+        return None, stuck
+    total = max(end_time)
+    return total / (nt / 2.0), sum(pipe_busy) / (2 * total)
