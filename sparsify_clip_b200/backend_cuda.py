@@ -19,6 +19,22 @@ _fp32_mode = "exact"
 _force_path = None  # testing hook: PATH_SIMT / PATH_TC / None
 
 
+# Every device buffer the backend hands to the library comes from these two hooks (PyTorch's caching allocator in
+# production).  tests/ swap them for a guarded allocator that surrounds each buffer with canaries and verifies, after the
+# kernels ran, that nothing wrote outside it.
+_empty = torch.empty
+_zeros = torch.zeros
+
+
+def set_allocator(empty_fn=None, zeros_fn=None):
+    """Test hook: replace the buffer allocators (None restores torch.empty / torch.zeros)."""
+    global _empty, _zeros
+    prev = (_empty, _zeros)
+    _empty = empty_fn or torch.empty
+    _zeros = zeros_fn or torch.zeros
+    return prev
+
+
 def set_fp32_mode(mode):
     global _fp32_mode
     if mode not in ("exact", "bf16"):
@@ -139,8 +155,8 @@ class CudaBackend:
 
     def sum(self, x):
         x = x.contiguous().view(-1)
-        out = torch.empty((), dtype=torch.float32, device=x.device)
-        scratch = torch.empty(1024, dtype=torch.float32, device=x.device)
+        out = _empty((), dtype=torch.float32, device=x.device)
+        scratch = _empty(1024, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             check(self.lib.scb_sum(_ptr(x), x.numel(), _ptr(scratch), _ptr(out), self._stream()), "sum")
         self._count(2)
@@ -148,7 +164,7 @@ class CudaBackend:
 
     # ------------------------------------------------------------------ row-wise
     def row_sqnorm(self, x):
-        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        out = _empty(x.shape[0], dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             check(self.lib.scb_row_sqnorm(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _DT[x.dtype], _ptr(out),
                                           self._stream()), "row_sqnorm")
@@ -156,7 +172,7 @@ class CudaBackend:
         return out
 
     def row_dot(self, a, b):
-        out = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+        out = _empty(a.shape[0], dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
             check(self.lib.scb_row_dot(_ptr(a), _ptr(b), a.shape[0], a.shape[1], a.stride(0), b.stride(0), _DT[a.dtype],
                                        _ptr(out), self._stream()), "row_dot")
@@ -164,7 +180,7 @@ class CudaBackend:
         return out
 
     def lalign_rows(self, x, y):
-        out = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        out = _empty(x.shape[0], dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             check(self.lib.scb_lalign_rows(_ptr(x), _ptr(y), x.shape[0], x.shape[1], x.stride(0), y.stride(0),
                                            _DT[x.dtype], _ptr(out), self._stream()), "lalign_rows")
@@ -173,8 +189,8 @@ class CudaBackend:
 
     def lalign_bwd(self, x, y, host_scale, dev_scale, want_x=True, want_y=True):
         n, D = x.shape
-        dX = torch.empty(n, D, dtype=torch.float32, device=x.device) if want_x else None
-        dY = torch.empty(n, D, dtype=torch.float32, device=x.device) if want_y else None
+        dX = _empty(n, D, dtype=torch.float32, device=x.device) if want_x else None
+        dY = _empty(n, D, dtype=torch.float32, device=x.device) if want_y else None
         with torch.cuda.device(x.device):
             check(self.lib.scb_lalign_bwd(_ptr(x), _ptr(y), n, D, x.stride(0), y.stride(0), _DT[x.dtype], host_scale,
                                           _ptr(dev_scale), 0, _ptr(dX), _ptr(dY), self._stream()), "lalign_bwd")
@@ -183,8 +199,8 @@ class CudaBackend:
 
     def centroid_fwd(self, a, b, out_dtype):
         n, D = a.shape
-        C = torch.empty(n, D, dtype=out_dtype, device=a.device)
-        inv = torch.empty(n, dtype=torch.float32, device=a.device)
+        C = _empty(n, D, dtype=out_dtype, device=a.device)
+        inv = _empty(n, dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
             check(self.lib.scb_centroid_fwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(C),
                                             _DT[out_dtype], _ptr(inv), self._stream()), "centroid_fwd")
@@ -193,8 +209,8 @@ class CudaBackend:
 
     def centroid_bwd(self, a, b, dC, inv, host_scale=1.0, dev_scale=None):
         n, D = a.shape
-        dA = torch.empty(n, D, dtype=torch.float32, device=a.device)
-        dB = torch.empty(n, D, dtype=torch.float32, device=a.device)
+        dA = _empty(n, D, dtype=torch.float32, device=a.device)
+        dB = _empty(n, D, dtype=torch.float32, device=a.device)
         with torch.cuda.device(a.device):
             check(self.lib.scb_centroid_bwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(dC),
                                             _ptr(inv), host_scale, _ptr(dev_scale), 0, _ptr(dA), _ptr(dB),
@@ -204,8 +220,8 @@ class CudaBackend:
 
     def normalize_fwd(self, x, out_dtype):
         n, D = x.shape
-        Y = torch.empty(n, D, dtype=out_dtype, device=x.device)
-        inv = torch.empty(n, dtype=torch.float32, device=x.device)
+        Y = _empty(n, D, dtype=out_dtype, device=x.device)
+        inv = _empty(n, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             check(self.lib.scb_normalize_fwd(_ptr(x), n, D, x.stride(0), _DT[x.dtype], _ptr(Y), _DT[out_dtype],
                                              _ptr(inv), self._stream()), "normalize_fwd")
@@ -214,7 +230,7 @@ class CudaBackend:
 
     def normalize_bwd(self, x, dY, inv):
         n, D = x.shape
-        dX = torch.empty(n, D, dtype=torch.float32, device=x.device)
+        dX = _empty(n, D, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             check(self.lib.scb_normalize_bwd(_ptr(x), n, D, x.stride(0), _DT[x.dtype], _ptr(dY), _ptr(inv), _ptr(dX),
                                              self._stream()), "normalize_bwd")
@@ -228,9 +244,9 @@ class CudaBackend:
         nB = Ball.shape[0]
         path = self.path_for(A, Ball)
         jp, nsub = self._plan(path, nA, nB, D, False, A.device)
-        pm = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device)
+        pm = _empty(jp * nsub, nA, dtype=torch.float32, device=A.device)
         pl = torch.empty_like(pm)
-        out = torch.empty(nA, dtype=torch.float32, device=A.device)
+        out = _empty(nA, dtype=torch.float32, device=A.device)
         with torch.cuda.device(A.device):
             with self._Timed(self, "lse"):
                 check(self.lib.scb_lse_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0), _DT[A.dtype],
@@ -254,11 +270,11 @@ class CudaBackend:
         n_strips = 4 * ((nA + 127) // 128)
         f32 = dict(dtype=torch.float32, device=dev)
         nsub = 4                      # the fused sweep runs 16 epilogue warps: four 32-column slices per tile
-        pm, pl = torch.empty(jp * nsub, nA, **f32), torch.empty(jp * nsub, nA, **f32)
-        cref, csum = torch.empty(n_strips, (nB + 31) // 32, **f32), torch.empty(n_strips, nB, **f32)
-        r, c = torch.empty(nA, **f32), torch.empty(nB, **f32)
-        flag = torch.empty(1, dtype=torch.int32, device=dev)
-        pm2, pl2 = torch.empty(jp2 * nsub2, nB, **f32), torch.empty(jp2 * nsub2, nB, **f32)
+        pm, pl = _empty(jp * nsub, nA, **f32), _empty(jp * nsub, nA, **f32)
+        cref, csum = _empty(n_strips, (nB + 31) // 32, **f32), _empty(n_strips, nB, **f32)
+        r, c = _empty(nA, **f32), _empty(nB, **f32)
+        flag = _empty(1, dtype=torch.int32, device=dev)
+        pm2, pl2 = _empty(jp2 * nsub2, nB, **f32), _empty(jp2 * nsub2, nB, **f32)
         sqa, sqb = self.row_sqnorm(A), self.row_sqnorm(Bm)
         st = self._stream()
         with torch.cuda.device(dev):
@@ -293,13 +309,13 @@ class CudaBackend:
         n_strips = 4 * ((nA + 127) // 128)
         f32 = dict(dtype=torch.float32, device=dev)
         nsub = 4
-        pm, pl = torch.empty(jp * nsub, nA, **f32), torch.empty(jp * nsub, nA, **f32)
-        cref, csum = torch.empty(n_strips, (nB + 31) // 32, **f32), torch.empty(n_strips, nB, **f32)
-        r, M, L = torch.empty(nA, **f32), torch.empty(nB, **f32), torch.empty(nB, **f32)
+        pm, pl = _empty(jp * nsub, nA, **f32), _empty(jp * nsub, nA, **f32)
+        cref, csum = _empty(n_strips, (nB + 31) // 32, **f32), _empty(n_strips, nB, **f32)
+        r, M, L = _empty(nA, **f32), _empty(nB, **f32), _empty(nB, **f32)
         nR = Bm_rows.shape[0]
-        c_exact = torch.zeros(nR, **f32)
-        flag = torch.empty(1, dtype=torch.int32, device=dev)
-        pm2, pl2 = torch.empty(jp2 * nsub2, nR, **f32), torch.empty(jp2 * nsub2, nR, **f32)
+        c_exact = _zeros(nR, **f32)
+        flag = _empty(1, dtype=torch.int32, device=dev)
+        pm2, pl2 = _empty(jp2 * nsub2, nR, **f32), _empty(jp2 * nsub2, nR, **f32)
         sqa, sqb = self.row_sqnorm(A_all), self.row_sqnorm(Bm_all)
         st = self._stream()
         with torch.cuda.device(dev):
@@ -327,9 +343,9 @@ class CudaBackend:
         nB = Ball.shape[0]
         path = self.path_for(A, Ball)
         jp, nsub = self._plan(path, nA, nB, D, True, A.device)
-        out = torch.empty(jp, nA, D, dtype=torch.float32, device=A.device)
-        ws = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
-        dA = torch.empty(nA, D, dtype=torch.float32, device=A.device)
+        out = _empty(jp, nA, D, dtype=torch.float32, device=A.device)
+        ws = _empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
+        dA = _empty(nA, D, dtype=torch.float32, device=A.device)
         with torch.cuda.device(A.device):
             with self._Timed(self, "anchor_grad"):
                 check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0),
@@ -349,8 +365,8 @@ class CudaBackend:
         nB = Ball.shape[0]
         path = self.path_for(A, Ball)
         jp, nsub = self._plan(path, nA, nB, D, True, A.device)
-        out = torch.empty(jp, nA, D, dtype=torch.float32, device=A.device)
-        ws = torch.empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
+        out = _empty(jp, nA, D, dtype=torch.float32, device=A.device)
+        ws = _empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
         with torch.cuda.device(A.device):
             with self._Timed(self, "anchor_grad"):
                 check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0),
@@ -364,7 +380,7 @@ class CudaBackend:
         """dX = a_coef (sum_p out[p] + dcoef Y) + u_coef (rq X - sum_p U[p]) + l_coef (X - Y), one streaming pass.
         anchor = dict(out, jparts, row_lse, col_lse_rows, diag, scale, coef); unif = dict(core, coef, dev_coef)."""
         n, D = X.shape
-        dX = torch.empty(n, D, dtype=out_dtype, device=X.device)
+        dX = _empty(n, D, dtype=out_dtype, device=X.device)
         a, u = anchor or {}, unif or {}
         core = u.get("core") or {}
         with torch.cuda.device(X.device):
@@ -389,12 +405,12 @@ class CudaBackend:
             sqn_all = self.row_sqnorm(Xall)
         if sqn_r is None:  # by contract Xr holds rows [row_offset, row_offset + nR) of Xall
             sqn_r = sqn_all[row_offset:row_offset + nR]
-        rs = torch.empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
+        rs = _empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
         core = {"jparts": jp, "nparts": jp * nsub, "path": path}
         with torch.cuda.device(Xr.device):
             if need_grad:
-                U = torch.empty(jp, nR, D, dtype=torch.float32, device=Xr.device)
-                rq = torch.empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
+                U = _empty(jp, nR, D, dtype=torch.float32, device=Xr.device)
+                rq = _empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
                 with self._Timed(self, "lunif"):
                     check(self.lib.scb_lunif_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),
                                                   _DT[Xr.dtype], float(t), _ptr(sqn_r), _ptr(sqn_all), int(row_offset), jp,
@@ -412,7 +428,7 @@ class CudaBackend:
     def lunif_grad(self, core, Xr, host_scale, dev_scale):
         """dX = s * (rq_i x_i - U_i), s = host_scale * dev_scale (0-dim device tensor)."""
         nR, D = Xr.shape
-        dX = torch.empty(nR, D, dtype=torch.float32, device=Xr.device)
+        dX = _empty(nR, D, dtype=torch.float32, device=Xr.device)
         with torch.cuda.device(Xr.device):
             check(self.lib.scb_lunif_grad_finalize(_ptr(core["U"]), core["jparts"], _ptr(core["rq"]), core["nparts"], nR, D,
                                                    _ptr(Xr), Xr.stride(0), _DT[Xr.dtype], float(host_scale), _ptr(dev_scale),
@@ -425,7 +441,7 @@ class CudaBackend:
         nAll = Xall.shape[0]
         path = self.path_for(Xr, Xall)
         jp, nsub = self._plan(path, nR, nAll, D, False, Xr.device)
-        rs = torch.empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
+        rs = _empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
         with torch.cuda.device(Xr.device):
             check(self.lib.scb_sparsify_sum_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),
                                                  _DT[Xr.dtype], int(row_offset), jp, _ptr(rs), path, self._stream()),
