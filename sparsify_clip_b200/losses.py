@@ -306,33 +306,29 @@ class _FusedTermsFn(torch.autograd.Function):
         if need_tau and w_a != 0.0:
             dt, tdev, shp = tau_t.dtype, tau_t.device, tau_t.shape
             dtau = (parts[4] * (-(w_a * scale * scale) / (2.0 * B))).to(device=tdev, dtype=dt).reshape(shp)
-        dI = dT = None
-        lc = 2.0 * w_l / B
+        # The per-operand combine runs in backward with grad_output as its device-side scale: one pass writes the final
+        # gradient in the input dtype (no separate multiply).  The sweep outputs stay alive until then.
         okdt = (torch.float32, torch.bfloat16, torch.float16)
-        if need_I:
-            dI = be.grad_combine(Ip, Tp, I.dtype if I.dtype in okdt else torch.float32, anchor=an_I, unif=un_I, l_coef=lc)
-        if need_T:
-            dT = be.grad_combine(Tp, Ip, T.dtype if T.dtype in okdt else torch.float32, anchor=an_T, unif=un_T, l_coef=lc)
         ctx.in_dtypes = (I.dtype, T.dtype)
-        ctx.has = (dI is not None, dT is not None, dtau is not None)
-        ctx.save_for_backward(*[x for x in (dI, dT, dtau) if x is not None])
+        ctx.out_dtypes = (I.dtype if I.dtype in okdt else torch.float32, T.dtype if T.dtype in okdt else torch.float32)
+        ctx.need = (need_I, need_T)
+        ctx.terms = (Ip, Tp, an_I, an_T, un_I, un_T, 2.0 * w_l / B)
+        ctx.dtau = dtau
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        saved = list(ctx.saved_tensors)
+        be = get_backend()
         g = _gout32(gout)
-        outs = []
-        for i, has in enumerate(ctx.has):
-            if not has:
-                outs.append(None)
-                continue
-            x = saved.pop(0)
-            if i < 2:
-                outs.append((x * g.to(x.dtype)).to(ctx.in_dtypes[i]))
-            else:
-                outs.append((x * g.to(device=x.device, dtype=x.dtype)))
-        return outs[0], outs[1], outs[2], None, None, None, None, None, None, None
+        Ip, Tp, an_I, an_T, un_I, un_T, lc = ctx.terms
+        dI = dT = dtau = None
+        if ctx.need[0]:
+            dI = be.grad_combine(Ip, Tp, ctx.out_dtypes[0], anchor=an_I, unif=un_I, l_coef=lc, dev_scale=g).to(ctx.in_dtypes[0])
+        if ctx.need[1]:
+            dT = be.grad_combine(Tp, Ip, ctx.out_dtypes[1], anchor=an_T, unif=un_T, l_coef=lc, dev_scale=g).to(ctx.in_dtypes[1])
+        if ctx.dtau is not None:
+            dtau = ctx.dtau * g.to(device=ctx.dtau.device, dtype=ctx.dtau.dtype)
+        return dI, dT, dtau, None, None, None, None, None, None, None
 
 
 def fused_terms_loss(image_embeds, text_embeds, temperature=0.07, w_anchor=1.0, w_align=0.0, w_unif_img=0.0,
