@@ -331,3 +331,34 @@ def test_kernels_stay_inside_their_buffers(B, D, tau, dtype):
     finally:
         backend_cuda.set_allocator(*prev)
     assert n > 20 and bad == 0, (bad, n)
+
+
+@pytest.mark.parametrize("scale_i,scale_t,tau,same", [(4.0, 3.0, 0.1, False), (1.0, 1.0, 0.1, True), (0.05, 20.0, 0.5, False),
+                                                      (1.0, 1.0, 0.02, False)])
+def test_unnormalised_and_degenerate_inputs(scale_i, scale_t, tau, same):
+    """Rows far from unit norm (logits of several hundred: the device-side norm bound must arm the exact column sweep),
+    I == T (every diagonal logit is its row's and column's maximum) and a small temperature, against the fp64 oracle."""
+    B, D = 300, 512
+    g = torch.Generator().manual_seed(3)
+    I = torch.randn(B, D, generator=g)
+    I = scale_i * I / I.norm(dim=1, keepdim=True) * (0.5 + torch.rand(B, 1, generator=g))
+    T = I.clone() if same else torch.randn(B, D, generator=g)
+    if not same:
+        T = scale_t * T / T.norm(dim=1, keepdim=True) * (0.5 + torch.rand(B, 1, generator=g))
+    I, T = I.to(torch.bfloat16).float(), T.to(torch.bfloat16).float()
+    prev = scb.set_fp32_mode("bf16")
+    try:
+        Ig, Tg = I.cuda().requires_grad_(True), T.cuda().requires_grad_(True)
+        tp = torch.nn.Parameter(torch.tensor(tau))
+        loss = scb.weighted_loss(Ig, Tg, tp, dict(anchor=1.0, align=0.0, unif_img=0.0, unif_txt=0.0, unif_cen=0.0))
+        loss.backward()
+    finally:
+        scb.set_fp32_mode(prev)
+    ref, dI, dT, dtau = cf.contrastive_loss(I.numpy(), T.numpy(), tau)
+    # the loss is mean(lse - diag): with I == T the two nearly cancel, so the bound is stated against the size of the
+    # terms (fp32 tensor-core accumulation truncates, ~1e-6 relative on each logit), not against the difference
+    diag_mag = float(np.abs((I.double() * T.double()).sum(1).numpy()).mean()) / tau
+    assert np.isfinite(loss.item()) and abs(loss.item() - ref) <= 1e-5 * abs(ref) + 2e-6 * diag_mag, (loss.item(), ref)
+    assert np.linalg.norm(Ig.grad.double().cpu().numpy() - dI) <= 2e-3 * np.linalg.norm(dI)
+    assert np.linalg.norm(Tg.grad.double().cpu().numpy() - dT) <= 2e-3 * np.linalg.norm(dT)
+    assert _rel(tp.grad.item(), dtau) <= 2e-3
