@@ -53,9 +53,15 @@ struct PairParams {
   float* s0;   // anchor: ws ; lunif: rq     [jparts*4][nA]
   float* s1;   // lunif: rs
   unsigned long long* trace;   // debug timeline (scb_debug_pair_trace), normally null
-  int dbg;                     // tuning/timing experiments: bit0 = send 1/16 of the W bytes (WRONG results);
-                               // bits 3.. = sender pace override in units of 50 cycles
+  int dbg;                     // sender pace override in units of 50 cycles (bits 3..), 0 = kSendPaceClk.  Builds with
+                               // -DSCB_PAIR_EXPERIMENTS also honour bit0 = send 1/16 of the W bytes (WRONG results,
+                               // timing experiments only); the shipped library ignores it.
 };
+#ifdef SCB_PAIR_EXPERIMENTS
+#define SCB_PAIR_SHORT_W(P) ((P).dbg & 1)
+#else
+#define SCB_PAIR_SHORT_W(P) 0
+#endif
 
 // Debug timeline: cluster 0 records (tag, tile, clock64) per role; kTraceCap events per (CTA rank, role).
 constexpr int kTraceCap = 4096;
@@ -359,7 +365,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           b = k2 & 1u;
           ptx::mbar_wait(bar(BAR_G_FULL + b), (k2 >> 1) & 1u, 220);
         } else {
-          if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL), (P.dbg & 1) ? 2048u : 2u * kSlotBytes);
+          if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL), SCB_PAIR_SHORT_W(P) ? 2048u : 2u * kSlotBytes);
           __syncwarp();
           ptx::mbar_wait(bar(BAR_W_FULL), kp & 1u, 225);
           ptx::fence_proxy_async_smem();
@@ -601,7 +607,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // ~3000 cycles per tile pair); spreading the 32 KB over ~3000 cycles costs nothing (the peer consumes the
         // tile kPeerLag steps later) and was the best of {0, 100, 200, 300, 400+} cycles per store.
         const int pace = (P.dbg >> 3) ? (P.dbg >> 3) * 50 : kSendPaceClk;
-        if (P.dbg & 1) {     // timing experiment: same handshake, 1/16 of the bytes
+        if (SCB_PAIR_SHORT_W(P)) {     // timing experiment: same handshake, 1/16 of the bytes
           st_async_v4(row_addr, w0[0], w0[1], w0[2], w0[3], peer_w_full);
           continue;
         }
