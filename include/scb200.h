@@ -171,14 +171,18 @@ int scb_lunif_grad_finalize(const float* U, int jparts, const float* rq, int npa
  * their gradients w.r.t. one operand are combined in a single pass, written in `out_dtype`):
  *   dX[i,:] = gs * ( a_coef * ( sum_p a_out[p][i,:] + (e^{sc*diag_i - row_lse_i} + e^{sc*diag_i - col_lse_i} - 2) * Y[i,:] )
  *                  + uc     * ( (sum_q rq[q][i]) * X[i,:] - sum_p u_out[p][i,:] )
- *                  + l_coef * ( X[i,:] - Y[i,:] ) )
- * gs = dev_scale ? *dev_scale : 1;  uc = u_coef * (u_dev_coef ? *u_dev_coef : 1).  a_out / u_out may be NULL
- * (term absent); l_coef == 0 skips L_align.  X = the operand's rows, Y = the paired rows of the other modality. */
+ *                  + l_coef * ( X[i,:] - Y[i,:] )
+ *                  + e_coef * extra[i,:] )
+ * gs = dev_scale ? *dev_scale : 1;  uc = u_coef * (u_dev_coef ? *u_dev_coef : 1).  a_out / u_out / extra may be NULL
+ * (term absent); l_coef == 0 skips L_align.  X = the operand's rows, Y = the paired rows of the other modality;
+ * extra = a finished contiguous fp32 [n, D] gradient term (the centroid chain of sparsify_clip.py:353/804: L_unif of
+ * the normalised centroids pulled back through the normalisation by scb_centroid_bwd). */
 int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
                      const float* a_out, int a_jparts, const float* row_lse, const float* col_lse_rows,
                      const float* diag, float scale, float a_coef, const float* u_out, int u_jparts,
                      const float* rq, int rq_parts, float u_coef, const float* u_dev_coef, float l_coef,
-                     const float* dev_scale, void* dX, int out_dtype, int64_t ldOut, void* stream);
+                     const float* extra, float e_coef, const float* dev_scale, void* dX, int out_dtype,
+                     int64_t ldOut, void* stream);
 
 /* sparsify_loss (sparsify_clip.py:166-176), forward: row partial sums of
  * (x_i.x_j - (2 delta_ij - 1))^2 over j; rs [jparts*nsub][nR]. */

@@ -207,10 +207,11 @@ class CudaBackend:
         self._count()
         return C, inv
 
-    def centroid_bwd(self, a, b, dC, inv, host_scale=1.0, dev_scale=None):
+    def centroid_bwd(self, a, b, dC, inv, host_scale=1.0, dev_scale=None, both=True):
+        """(dA, dB): the two are equal element for element; both=False writes one array and returns (dA, None)."""
         n, D = a.shape
         dA = _empty(n, D, dtype=torch.float32, device=a.device)
-        dB = _empty(n, D, dtype=torch.float32, device=a.device)
+        dB = _empty(n, D, dtype=torch.float32, device=a.device) if both else None
         with torch.cuda.device(a.device):
             check(self.lib.scb_centroid_bwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(dC),
                                             _ptr(inv), host_scale, _ptr(dev_scale), 0, _ptr(dA), _ptr(dB),
@@ -376,9 +377,12 @@ class CudaBackend:
         self._count()
         return {"out": out, "jparts": jp, "ws": self.sum(ws) if want_ws else None}
 
-    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None):
-        """dX = a_coef (sum_p out[p] + dcoef Y) + u_coef (rq X - sum_p U[p]) + l_coef (X - Y), one streaming pass.
-        anchor = dict(out, jparts, row_lse, col_lse_rows, diag, scale, coef); unif = dict(core, coef, dev_coef)."""
+    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None, extra=None, e_coef=0.0):
+        """dX = a_coef (sum_p out[p] + dcoef Y) + u_coef (rq X - sum_p U[p]) + l_coef (X - Y) + e_coef extra, one
+        streaming pass.  anchor = dict(out, jparts, row_lse, col_lse_rows, diag, scale, coef);
+        unif = dict(core, coef, dev_coef); extra = contiguous fp32 [n, D]."""
+        if extra is not None:
+            assert extra.dtype == torch.float32 and extra.is_contiguous() and extra.shape == X.shape
         n, D = X.shape
         dX = _empty(n, D, dtype=out_dtype, device=X.device)
         a, u = anchor or {}, unif or {}
@@ -389,8 +393,8 @@ class CudaBackend:
                 _ptr(a.get("out")), int(a.get("jparts", 0)), _ptr(a.get("row_lse")), _ptr(a.get("col_lse_rows")),
                 _ptr(a.get("diag")), float(a.get("scale", 0.0)), float(a.get("coef", 0.0)),
                 _ptr(core.get("U")), int(core.get("jparts", 0)), _ptr(core.get("rq")), int(core.get("nparts", 0)),
-                float(u.get("coef", 0.0)), _ptr(u.get("dev_coef")), float(l_coef), _ptr(dev_scale),
-                _ptr(dX), _DT[out_dtype], dX.stride(0), self._stream()), "grad_combine")
+                float(u.get("coef", 0.0)), _ptr(u.get("dev_coef")), float(l_coef), _ptr(extra), float(e_coef),
+                _ptr(dev_scale), _ptr(dX), _DT[out_dtype], dX.stride(0), self._stream()), "grad_combine")
         self._count()
         return dX
 

@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(kThreads) k_lunif_fin(const float* __restrict_
 // One pass over an operand that applies every term of the composed loss at once:
 //   dX[i,:] = gs * ( a_coef * ( sum_p a_out[p][i,:] + dcoef_i * Y[i,:] )          anchor  (dcoef_i = P_ii + Q_ii - 2)
 //                  + u_coef * ( (sum_q rq[q][i]) * X[i,:] - sum_p u_out[p][i,:] )  L_unif
-//                  + l_coef * ( X[i,:] - Y[i,:] ) )                                L_align
+//                  + l_coef * ( X[i,:] - Y[i,:] )                                  L_align
+//                  + e_coef * extra[i,:] )                                         a finished fp32 term (centroid chain)
 // Each thread owns 8 consecutive columns of one row (16-byte loads of every partial, one 16/32-byte store), so the
 // kernel streams at HBM speed; the per-row scalars are recomputed per thread (a few L1-resident loads).
 struct CombineArgs {
@@ -363,6 +364,7 @@ struct CombineArgs {
   float a_coef;
   const float* u_out; int u_jparts; const float* rq; int rq_parts; float u_coef; const float* u_dev_coef;
   float l_coef;
+  const float* extra; float e_coef;
   const float* dev_scale;
   void* dX; int out_dtype; int64_t ldOut;
 };
@@ -425,6 +427,18 @@ __global__ void __launch_bounds__(256) k_grad_combine(const CombineArgs a) {
     }
 #pragma unroll
     for (int i = 0; i < W; ++i) g[i] = fmaf(uc, acc[i], g[i]);
+  }
+  if (a.extra) {
+    const float* src = a.extra + o;
+    if (VEC) {
+      const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src)), v1 = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+      g[0] = fmaf(a.e_coef, v0.x, g[0]); g[1] = fmaf(a.e_coef, v0.y, g[1]);
+      g[2] = fmaf(a.e_coef, v0.z, g[2]); g[3] = fmaf(a.e_coef, v0.w, g[3]);
+      g[4] = fmaf(a.e_coef, v1.x, g[4]); g[5] = fmaf(a.e_coef, v1.y, g[5]);
+      g[6] = fmaf(a.e_coef, v1.z, g[6]); g[7] = fmaf(a.e_coef, v1.w, g[7]);
+    } else {
+      g[0] = fmaf(a.e_coef, __ldcs(src), g[0]);
+    }
   }
   if (a.dev_scale) {
     const float gs = __ldg(a.dev_scale);
@@ -604,7 +618,8 @@ extern "C" int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, 
                                 const float* a_out, int a_jparts, const float* row_lse, const float* col_lse_rows,
                                 const float* diag, float scale, float a_coef, const float* u_out, int u_jparts,
                                 const float* rq, int rq_parts, float u_coef, const float* u_dev_coef, float l_coef,
-                                const float* dev_scale, void* dX, int out_dtype, int64_t ldOut, void* stream) {
+                                const float* extra, float e_coef, const float* dev_scale, void* dX, int out_dtype,
+                                int64_t ldOut, void* stream) {
   SCB_COMMON_CHECKS(X && dX, n, D, dtype);
   SCB_CHECK_ARG(scb_dtype_ok(out_dtype) && ldOut >= D, SCB_E_ARG, "grad_combine: bad output layout");
   SCB_CHECK_ARG(!a_out || (Y && row_lse && col_lse_rows && diag && a_jparts > 0), SCB_E_ARG, "grad_combine: anchor term");
@@ -612,9 +627,10 @@ extern "C" int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, 
   SCB_CHECK_ARG(l_coef == 0.f || Y, SCB_E_ARG, "grad_combine: L_align term needs Y");
   if (n == 0) return 0;
   CombineArgs a{X, Y, n, D, ldX, ldY, dtype, a_out, a_jparts, row_lse, col_lse_rows, diag, scale, a_coef, u_out, u_jparts,
-                rq, rq_parts, u_coef, u_dev_coef, l_coef, dev_scale, dX, out_dtype, ldOut};
+                rq, rq_parts, u_coef, u_dev_coef, l_coef, extra, e_coef, dev_scale, dX, out_dtype, ldOut};
   cudaStream_t s = (cudaStream_t)stream;
-  const bool vec = vec_ok(X, ldX, D) && (!Y || vec_ok(Y, ldY, D)) && scb_aligned16(dX) && ldOut % 8 == 0;
+  const bool vec = vec_ok(X, ldX, D) && (!Y || vec_ok(Y, ldY, D)) && scb_aligned16(dX) && ldOut % 8 == 0 &&
+                   (!extra || scb_aligned16(extra));
   const int per_row = vec ? D / 8 : D;
   const int64_t total = n * per_row;
   const unsigned grid = (unsigned)((total + 255) / 256);

@@ -81,7 +81,7 @@ _fuse = True
 
 
 def set_fused(flag):
-    """Evaluate centroid-free compositions as one fused autograd node (default) or term by term."""
+    """Evaluate the compositions as one fused autograd node (default) or term by term."""
     global _fuse
     prev, _fuse = _fuse, bool(flag)
     return prev
@@ -89,9 +89,9 @@ def set_fused(flag):
 
 def weighted_loss(image_embeds, text_embeds, temperature, w, *, group=None):
     """sum of the selected terms; a zero weight skips the kernel (its gradient is exactly 0)."""
-    if _fuse and w["unif_cen"] == 0.0 and (w["anchor"] != 0.0 or w["align"] != 0.0 or w["unif_img"] != 0.0 or w["unif_txt"] != 0.0):
+    if _fuse and any(w[k] != 0.0 for k in ("anchor", "align", "unif_img", "unif_txt", "unif_cen")):
         return fused_terms_loss(image_embeds, text_embeds, temperature, w["anchor"], w["align"], w["unif_img"],
-                                w["unif_txt"], group=group)
+                                w["unif_txt"], w_unif_cen=w["unif_cen"], group=group)
     loss = None
 
     def add(acc, wt, term):

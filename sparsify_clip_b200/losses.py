@@ -185,7 +185,7 @@ def lunif_loss(x, t=2, *, group=None, mma_dtype=None):
 # ----------------------------------------------------------------------------- fused composition
 class _FusedTermsFn(torch.autograd.Function):
     """w_a * contrastive_loss(I, T, tau) + w_l * lalign_loss(I, T) + w_i * lunif_loss(I) + w_t * lunif_loss(T)
-    (the compositions of sparsify_clip.py:778-938 that do not involve centroids) as ONE autograd node.
+    + w_c * lunif_loss(normalize((I + T) / 2))  (every composition of sparsify_clip.py:778-938) as ONE autograd node.
 
     Same B x B passes as the separate functions; what is fused is everything around them: the per-term gradient
     finalisers, the dtype casts and autograd's accumulation of the terms collapse into one streaming pass per
@@ -193,7 +193,7 @@ class _FusedTermsFn(torch.autograd.Function):
     forward (L_unif yields it in the same sweep as its value anyway); backward multiplies by grad_output."""
 
     @staticmethod
-    def forward(ctx, I, T, tau_t, tau_f, w_a, w_l, w_i, w_t, t_unif, group):
+    def forward(ctx, I, T, tau_t, tau_f, w_a, w_l, w_i, w_t, w_c, t_unif, group):
         be = get_backend()
         I, T = _common(I, T)
         Ip, Tp = be.prep(I), be.prep(T)
@@ -206,6 +206,14 @@ class _FusedTermsFn(torch.autograd.Function):
         need = need_I or need_T
         # ---- exchange step 1: the operands (both gathers in flight together)
         I_all, T_all, pending = Ip, Tp, []
+        # normalised centroids (sparsify_clip.py:353 + :804): fp32 master copy C, tensor-core operand Cq (see
+        # centroid_operand_dtype: fp16 keeps the term inside the parity gates where bf16 does not)
+        C = Cq = C_all = c_inv = None
+        if w_c != 0.0:
+            C, c_inv = be.centroid_fwd(Ip, Tp, torch.float32)
+            cdt = torch.float16 if Ip.dtype in (torch.bfloat16, torch.float16) else Ip.dtype
+            Cq = C.to(cdt) if C.dtype != cdt else C
+            C_all = Cq
         if group is not None:
             if w_a != 0.0 or w_i != 0.0:
                 I_all, h = _all_gather_rows_async(Ip, group)
@@ -213,9 +221,14 @@ class _FusedTermsFn(torch.autograd.Function):
             if w_a != 0.0 or w_t != 0.0:
                 T_all, h = _all_gather_rows_async(Tp, group)
                 pending.append(h)
+            if w_c != 0.0:
+                C_all, h = _all_gather_rows_async(Cq, group)
+                pending.append(h)
         # scalar partial sums of this rank
-        #   0: anchor (sum r + sum c - 2/tau sum diag)   1: L_align   2, 3: L_unif row sums (I, T)   4: d/dtau
-        parts = torch.zeros(5, dtype=torch.float32, device=dev)
+        #   0: anchor (sum r + sum c - 2/tau sum diag)   1: L_align   2, 3, 4: L_unif row sums (I, T, centroids)
+        #   5: d/dtau
+        NS = 5                                               # how many of them travel in the packed gather
+        parts = torch.zeros(NS + 1, dtype=torch.float32, device=dev)
         if w_l != 0.0:
             parts[1] = be.sum(be.lalign_rows(Ip, Tp))
         for h in pending:
@@ -244,7 +257,8 @@ class _FusedTermsFn(torch.autograd.Function):
                 parts[0] = parts[0] + be.sum(c)
         un_I = un_T = None
         cores = {}
-        for (wu, Xp, X_all, needx, which, slot) in ((w_i, Ip, I_all, need_I, "I", 2), (w_t, Tp, T_all, need_T, "T", 3)):
+        for (wu, Xp, X_all, needx, which, slot) in ((w_i, Ip, I_all, need_I, "I", 2), (w_t, Tp, T_all, need_T, "T", 3),
+                                                    (w_c, Cq, C_all, need, "C", 4)):
             if wu == 0.0:
                 continue
             core = be.lunif_core(Xp, X_all, float(t_unif), off, needx)
@@ -257,19 +271,19 @@ class _FusedTermsFn(torch.autograd.Function):
         gathered = False
         if group is not None and w_a != 0.0 and (need or need_tau or colparts is not None):
             if colparts is None:
-                pieces = (r, c, parts[:4])
+                pieces = (r, c, parts[:NS])
             else:
                 _, cM, cL, c_exact, flag = colparts
-                pieces = (r, c_exact, parts[:4], cM, cL)
+                pieces = (r, c_exact, parts[:NS], cM, cL)
             pack = torch.cat([x.to(torch.float32) for x in pieces])
             pack_flat = torch.empty(ws * pack.numel(), dtype=torch.float32, device=dev)
             dist.all_gather_into_tensor(pack_flat, pack, group=group)
             pack_all = pack_flat.view(ws, -1)
             r_all = pack_all[:, :n].reshape(-1)
             c_all = pack_all[:, n:2 * n].reshape(-1)
-            parts = torch.cat((pack_all[:, 2 * n:2 * n + 4].sum(0), parts[4:]))
+            parts = torch.cat((pack_all[:, 2 * n:2 * n + NS].sum(0), parts[NS:]))
             if colparts is not None:
-                Mr, Lr = pack_all[:, 2 * n + 4:2 * n + 4 + B], pack_all[:, 2 * n + 4 + B:]
+                Mr, Lr = pack_all[:, 2 * n + NS:2 * n + NS + B], pack_all[:, 2 * n + NS + B:]
                 Mx = Mr.max(0).values
                 c_fused = (Mx + torch.log2((Lr * torch.exp2(Mr - Mx)).sum(0))) * math.log(2.0)
                 c_all = torch.where(flag != 0, c_all, c_fused)          # exact second sweep where the bound demanded it
@@ -282,7 +296,7 @@ class _FusedTermsFn(torch.autograd.Function):
                 p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
                 an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef)
                 if need_tau:
-                    parts[4] = p["ws"] - 2.0 * sdiag
+                    parts[NS] = p["ws"] - 2.0 * sdiag
             if need_T:
                 p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
                 an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
@@ -291,28 +305,34 @@ class _FusedTermsFn(torch.autograd.Function):
             if not gathered:
                 _all_reduce_(parts, group)
             elif need_tau:
-                _all_reduce_(parts[4:], group)
+                _all_reduce_(parts[NS:], group)
         loss = (w_a / (2.0 * B)) * parts[0] + (w_l / B) * parts[1]
+        cen = None
         for which, (core, wu, needx) in cores.items():
-            ssum = parts[2 if which == "I" else 3] * 0.5
+            ssum = parts[{"I": 2, "T": 3, "C": 4}[which]] * 0.5
             loss = loss + wu * torch.log(ssum / (B * (B - 1) / 2.0))      # B == 1 -> nan, as the reference
             if needx:
                 u = dict(core=core, coef=wu * (-2.0 * float(t_unif)), dev_coef=torch.reciprocal(ssum).reshape(1).contiguous())
                 if which == "I":
                     un_I = u
-                else:
+                elif which == "T":
                     un_T = u
+                else:
+                    # the centroid chain: L_unif gradient at the unrounded centroids, pulled back through
+                    # normalize((I + T) / 2); the result is the same array for both operands
+                    gC = be.lunif_grad(core, C, u["coef"], u["dev_coef"])
+                    cen = be.centroid_bwd(Ip, Tp, gC, c_inv, both=False)[0]
         dtau = None
         if need_tau and w_a != 0.0:
             dt, tdev, shp = tau_t.dtype, tau_t.device, tau_t.shape
-            dtau = (parts[4] * (-(w_a * scale * scale) / (2.0 * B))).to(device=tdev, dtype=dt).reshape(shp)
+            dtau = (parts[NS] * (-(w_a * scale * scale) / (2.0 * B))).to(device=tdev, dtype=dt).reshape(shp)
         # The per-operand combine runs in backward with grad_output as its device-side scale: one pass writes the final
         # gradient in the input dtype (no separate multiply).  The sweep outputs stay alive until then.
         okdt = (torch.float32, torch.bfloat16, torch.float16)
         ctx.in_dtypes = (I.dtype, T.dtype)
         ctx.out_dtypes = (I.dtype if I.dtype in okdt else torch.float32, T.dtype if T.dtype in okdt else torch.float32)
         ctx.need = (need_I, need_T)
-        ctx.terms = (Ip, Tp, an_I, an_T, un_I, un_T, 2.0 * w_l / B)
+        ctx.terms = (Ip, Tp, an_I, an_T, un_I, un_T, 2.0 * w_l / B, cen)
         ctx.dtau = dtau
         return loss
 
@@ -320,26 +340,29 @@ class _FusedTermsFn(torch.autograd.Function):
     def backward(ctx, gout):
         be = get_backend()
         g = _gout32(gout)
-        Ip, Tp, an_I, an_T, un_I, un_T, lc = ctx.terms
+        Ip, Tp, an_I, an_T, un_I, un_T, lc, cen = ctx.terms
         dI = dT = dtau = None
         if ctx.need[0]:
-            dI = be.grad_combine(Ip, Tp, ctx.out_dtypes[0], anchor=an_I, unif=un_I, l_coef=lc, dev_scale=g).to(ctx.in_dtypes[0])
+            dI = be.grad_combine(Ip, Tp, ctx.out_dtypes[0], anchor=an_I, unif=un_I, l_coef=lc, dev_scale=g,
+                                 extra=cen, e_coef=1.0).to(ctx.in_dtypes[0])
         if ctx.need[1]:
-            dT = be.grad_combine(Tp, Ip, ctx.out_dtypes[1], anchor=an_T, unif=un_T, l_coef=lc, dev_scale=g).to(ctx.in_dtypes[1])
+            dT = be.grad_combine(Tp, Ip, ctx.out_dtypes[1], anchor=an_T, unif=un_T, l_coef=lc, dev_scale=g,
+                                 extra=cen, e_coef=1.0).to(ctx.in_dtypes[1])
         if ctx.dtau is not None:
             dtau = ctx.dtau * g.to(device=ctx.dtau.device, dtype=ctx.dtau.dtype)
-        return dI, dT, dtau, None, None, None, None, None, None, None
+        return dI, dT, dtau, None, None, None, None, None, None, None, None
 
 
 def fused_terms_loss(image_embeds, text_embeds, temperature=0.07, w_anchor=1.0, w_align=0.0, w_unif_img=0.0,
-                     w_unif_txt=0.0, t=2, *, group=None):
-    """w_anchor * contrastive_loss + w_align * lalign_loss + w_unif_img * lunif_loss(I) + w_unif_txt * lunif_loss(T),
-    evaluated as one fused autograd node (see _FusedTermsFn).  Zero weights skip their kernels."""
+                     w_unif_txt=0.0, t=2, *, w_unif_cen=0.0, group=None):
+    """w_anchor * contrastive_loss + w_align * lalign_loss + w_unif_img * lunif_loss(I) + w_unif_txt * lunif_loss(T)
+    + w_unif_cen * lunif_loss(normalized_centroids(I, T)), evaluated as one fused autograd node (see _FusedTermsFn).
+    Zero weights skip their kernels."""
     group = _resolve_group(group)
     tt = temperature if isinstance(temperature, torch.Tensor) else None
     tf = None if tt is not None else float(temperature)
     return _FusedTermsFn.apply(image_embeds, text_embeds, tt, tf, float(w_anchor), float(w_align), float(w_unif_img),
-                               float(w_unif_txt), t, group)
+                               float(w_unif_txt), float(w_unif_cen), t, group)
 
 
 # ----------------------------------------------------------------------------- L_align

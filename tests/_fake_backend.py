@@ -37,11 +37,11 @@ class FakeBackend:
         inv = 1.0 / m.norm(dim=1).clamp_min(1e-12)
         return m * inv[:, None], inv
 
-    def centroid_bwd(self, a, b, dC, inv, host_scale=1.0, dev_scale=None):
+    def centroid_bwd(self, a, b, dC, inv, host_scale=1.0, dev_scale=None, both=True):
         c = (a + b) / 2 * inv[:, None]
         dC = dC.double()
         dm = (dC - c * (c * dC).sum(1, keepdim=True)) * inv[:, None] * 0.5 * host_scale
-        return dm, dm.clone()
+        return dm, (dm.clone() if both else None)
 
     def lse(self, A, Ball, scale):
         return torch.logsumexp(scale * A @ Ball.t(), dim=1)
@@ -80,8 +80,10 @@ class FakeBackend:
         W[idx, idx + diag_off] = 0
         return {"out": (W @ Ball)[None], "jparts": 1, "ws": ws}
 
-    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None):
+    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None, extra=None, e_coef=0.0):
         g = l_coef * (X - Y) if l_coef != 0.0 else torch.zeros_like(X)
+        if extra is not None:
+            g = g + e_coef * extra
         if anchor:
             sii = anchor["scale"] * anchor["diag"]
             dcoef = torch.exp(sii - anchor["row_lse"]) + torch.exp(sii - anchor["col_lse_rows"]) - 2

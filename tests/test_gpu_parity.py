@@ -245,7 +245,9 @@ def test_fused_composition_equals_the_sum_of_its_terms(B, D, dtype):
     for w in (dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0),
               dict(anchor=1.0, align=1.3, unif_img=0.1, unif_txt=0.1, unif_cen=0.0),
               dict(anchor=0.0, align=0.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0),
-              dict(anchor=1.0, align=0.0, unif_img=0.0, unif_txt=0.0, unif_cen=0.0)):
+              dict(anchor=1.0, align=0.0, unif_img=0.0, unif_txt=0.0, unif_cen=0.0),
+              dict(anchor=1.0, align=1.0, unif_img=0.0, unif_txt=0.0, unif_cen=1.0),      # exp 4 / 10: centroid chain
+              dict(anchor=1.0, align=0.7, unif_img=0.25, unif_txt=0.25, unif_cen=0.5)):
         res = []
         for fused in (True, False):
             prev = scb.set_fused(fused)

@@ -21,6 +21,7 @@ for (B, D, tau, w) in [(1024, 512, 0.1, dict(anchor=1.0, align=1.0, unif_img=0.5
                        (2048, 768, 0.07, dict(anchor=1.0, align=1.3, unif_img=0.0, unif_txt=0.0, unif_cen=0.6)),
                        # tau = 0.02: the device-side norm bound arms the exact second LSE sweep on every rank
                        (1024, 512, 0.02, dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0)),
+                       (2048, 512, 0.1, dict(anchor=1.0, align=1.0, unif_img=0.0, unif_txt=0.0, unif_cen=1.0)),
                        (8192, 512, 0.1, dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0))]:
     g = torch.Generator(device=dev).manual_seed(1234)          # same full batch on every rank
     I = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device=dev), dim=-1)
