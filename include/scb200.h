@@ -125,6 +125,12 @@ int scb_colstat_combine(const float* col_ref, const float* col_sum, int nparts, 
  * all-gather these pairs (each rank sweeps its rows against all columns) and fold them once more. */
 int scb_colstat_partial(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* ref_out, float* sum_out,
                         void* stream);
+/* That second fold, after the packed gather of a sharded step (losses.py, exchange step 2).  pack = [world][stride]
+ * fp32, one row per rank: at off_exact the exact column LSE of the rank's own n_loc columns, at off_ref / off_sum its
+ * (reference, sum) pair for every one of the world * n_loc columns.  col_lse[j] = the exact value when *flag != 0
+ * (the norm bound armed the second sweep on every rank), else ln2 * (M + log2 sum_r sum_r[j] 2^(ref_r[j] - M)). */
+int scb_lse2_fold_ranks(const float* pack, int world, int64_t stride, int64_t n_loc, int64_t off_exact, int64_t off_ref,
+                        int64_t off_sum, const int* flag, float* col_lse, void* stream);
 /* *flag = (2 * scale * log2(e) * max_i |A_i| * max_j |B_j| >= 90) from the squared row norms (scb_row_sqnorm). */
 int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* sqnB, int64_t nB, float scale, int* flag, void* stream);
 /* scb_lse_pass / scb_lse_combine that do nothing unless *run_flag != 0 (device pointer). */

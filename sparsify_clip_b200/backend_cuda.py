@@ -336,6 +336,18 @@ class CudaBackend:
         self._count(6)
         return r, M, L, c_exact, flag
 
+    def lse2_fold_ranks(self, pack_all, n_loc, off_exact, off_ref, off_sum, flag):
+        """Column LSE of all world * n_loc columns from the gathered per-rank rows of `pack_all` [world, width]
+        (see scb_lse2_fold_ranks): one launch instead of ~9 element-wise ones."""
+        ws, width = pack_all.shape
+        assert pack_all.dtype == torch.float32 and pack_all.is_contiguous()
+        out = _empty(ws * n_loc, dtype=torch.float32, device=pack_all.device)
+        with torch.cuda.device(pack_all.device):
+            check(self.lib.scb_lse2_fold_ranks(_ptr(pack_all), ws, width, n_loc, off_exact, off_ref, off_sum, _ptr(flag),
+                                               _ptr(out), self._stream()), "lse2_fold_ranks")
+        self._count()
+        return out
+
     def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off,
                     host_scale, dev_scale, want_ws):
         """dA = s * [ sum_j (P_ij + Q_ij) Ball_j  (j != diagonal)  +  (P_ii + Q_ii - 2) V_i ]  (fp32 [nA, D]);

@@ -275,6 +275,28 @@ __global__ void __launch_bounds__(256) k_colstat_fold(const float* __restrict__ 
   }
 }
 
+// Fold of the per-rank column partials after the packed gather of a sharded step.  pack = [world][stride] fp32, one row
+// per rank: at off_exact the exact column LSE of that rank's own n_loc columns (valid when *flag != 0), at off_ref /
+// off_sum that rank's (reference, sum) partial of every one of the world * n_loc columns (log2 domain).
+__global__ void __launch_bounds__(256) k_fold_ranks(const float* __restrict__ pack, int world, int64_t stride, int64_t n_loc,
+                                                    int64_t off_exact, int64_t off_ref, int64_t off_sum,
+                                                    const int* __restrict__ flag, float* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= n_loc * world) return;
+  if (*flag != 0) {
+    out[j] = pack[(j / n_loc) * stride + off_exact + j % n_loc];
+    return;
+  }
+  float Mx = -INFINITY;
+  for (int r = 0; r < world; ++r) Mx = fmaxf(Mx, pack[r * stride + off_ref + j]);
+  float Ls = 0.f;
+  for (int r = 0; r < world; ++r) {
+    const float m = pack[r * stride + off_ref + j];
+    if (m != -INFINITY) Ls += pack[r * stride + off_sum + j] * exp2f(m - Mx);
+  }
+  out[j] = (Mx + log2f(Ls)) * SCB_LN2;
+}
+
 // flag = 1 when the logits can spread by more than `bound` (log2 units) inside one block of the fused pass:
 // 2 * scale * log2e * max_i |a_i| * max_j |b_j| >= bound   (sqn = squared row norms)
 __global__ void __launch_bounds__(1024) k_spread_flag(const float* __restrict__ sqnA, int64_t nA, const float* __restrict__ sqnB,
@@ -662,6 +684,20 @@ extern "C" int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* 
   SCB_CHECK_ARG(sqnA && sqnB && flag && nA >= 0 && nB >= 0 && scale > 0.f, SCB_E_ARG, "lse2_spread_flag: bad argument");
   k_spread_flag<<<1, 1024, 0, (cudaStream_t)stream>>>(sqnA, nA, sqnB, nB, scale, 90.f, flag);
   SCB_CHECK_LAUNCH("lse2_spread_flag");
+  return 0;
+}
+
+extern "C" int scb_lse2_fold_ranks(const float* pack, int world, int64_t stride, int64_t n_loc, int64_t off_exact,
+                                   int64_t off_ref, int64_t off_sum, const int* flag, float* col_lse, void* stream) {
+  SCB_CHECK_ARG(pack && flag && col_lse && world > 0 && n_loc >= 0, SCB_E_ARG, "lse2_fold_ranks: bad argument");
+  const int64_t B = n_loc * world;
+  SCB_CHECK_ARG(off_exact >= 0 && off_exact + n_loc <= stride && off_ref >= 0 && off_ref + B <= stride && off_sum >= 0 &&
+                    off_sum + B <= stride,
+                SCB_E_ARG, "lse2_fold_ranks: offsets outside the packed row");
+  if (B == 0) return 0;
+  k_fold_ranks<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pack, world, stride, n_loc, off_exact, off_ref,
+                                                                              off_sum, flag, col_lse);
+  SCB_CHECK_LAUNCH("lse2_fold_ranks");
   return 0;
 }
 

@@ -280,14 +280,13 @@ class _FusedTermsFn(torch.autograd.Function):
             dist.all_gather_into_tensor(pack_flat, pack, group=group)
             pack_all = pack_flat.view(ws, -1)
             r_all = pack_all[:, :n].reshape(-1)
-            c_all = pack_all[:, n:2 * n].reshape(-1)
             parts = torch.cat((pack_all[:, 2 * n:2 * n + NS].sum(0), parts[NS:]))
-            if colparts is not None:
-                Mr, Lr = pack_all[:, 2 * n + NS:2 * n + NS + B], pack_all[:, 2 * n + NS + B:]
-                Mx = Mr.max(0).values
-                c_fused = (Mx + torch.log2((Lr * torch.exp2(Mr - Mx)).sum(0))) * math.log(2.0)
-                c_all = torch.where(flag != 0, c_all, c_fused)          # exact second sweep where the bound demanded it
-                c = c_all[off:off + n].contiguous()
+            if colparts is None:
+                c_all = pack_all[:, n:2 * n].reshape(-1)
+            else:
+                # fold the column partials of all ranks (or take the exact second sweep where the bound demanded it)
+                c_all = be.lse2_fold_ranks(pack_all, n, n, 2 * n + NS, 2 * n + NS + B, flag)
+                c = c_all[off:off + n]
                 parts[0] = parts[0] + c_all.sum()
             gathered = True
         if w_a != 0.0 and (need or need_tau):

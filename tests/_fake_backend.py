@@ -2,6 +2,8 @@
 dense torch fp64 CPU math (oracle formulas).  Lets the CPU suite exercise the host logic of
 losses.py -- sharding offsets, all-gathers, scalar assembly, autograd wiring -- under gloo.
 Never imported by the product."""
+import math
+
 import torch
 
 
@@ -42,6 +44,14 @@ class FakeBackend:
         dC = dC.double()
         dm = (dC - c * (c * dC).sum(1, keepdim=True)) * inv[:, None] * 0.5 * host_scale
         return dm, (dm.clone() if both else None)
+
+    def lse2_fold_ranks(self, pack_all, n_loc, off_exact, off_ref, off_sum, flag):
+        B = pack_all.shape[0] * n_loc
+        if int(flag.item()) != 0:
+            return pack_all[:, off_exact:off_exact + n_loc].reshape(-1)
+        Mr, Lr = pack_all[:, off_ref:off_ref + B], pack_all[:, off_sum:off_sum + B]
+        Mx = Mr.max(0).values
+        return (Mx + torch.log2((Lr * torch.exp2(Mr - Mx)).sum(0))) * math.log(2.0)
 
     def lse(self, A, Ball, scale):
         return torch.logsumexp(scale * A @ Ball.t(), dim=1)

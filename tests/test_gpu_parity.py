@@ -4,6 +4,8 @@ i.e. through the C ABI of libscb200.so; the oracle (tests/golden + oracle/closed
 Tolerances: losses 1e-5 relative; gradients 1e-5 relative on the fp32 (SIMT, "tf32-off")
 path and 1e-3 relative on the bf16 tensor-core path; relative = Frobenius norm of the difference / norm of
 the reference (and per sampled row for the fixtures that store sampled rows only)."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -364,3 +366,27 @@ def test_unnormalised_and_degenerate_inputs(scale_i, scale_t, tau, same):
     assert np.linalg.norm(Ig.grad.double().cpu().numpy() - dI) <= 2e-3 * np.linalg.norm(dI)
     assert np.linalg.norm(Tg.grad.double().cpu().numpy() - dT) <= 2e-3 * np.linalg.norm(dT)
     assert _rel(tp.grad.item(), dtau) <= 2e-3
+
+
+@pytest.mark.parametrize("world,n_loc", [(2, 300), (8, 129), (1, 64)])
+def test_rank_fold_of_column_partials(world, n_loc):
+    """scb_lse2_fold_ranks against the log-sum-exp it restates, on a synthetic packed gather (both flag states)."""
+    be = scb.get_backend()
+    g = torch.Generator(device="cuda").manual_seed(world * 1000 + n_loc)
+    B, NS = world * n_loc, 5
+    width = 2 * n_loc + NS + 2 * B
+    pack = torch.randn(world, width, generator=g, device="cuda")
+    off_ref, off_sum = 2 * n_loc + NS, 2 * n_loc + NS + B
+    pack[:, off_ref:off_ref + B] *= 30.0                                   # references tens of log2 units apart
+    pack[:, off_sum:off_sum + B] = pack[:, off_sum:off_sum + B].abs() + 0.5
+    if world > 1:
+        pack[0, off_ref + 3] = float("-inf")                               # a rank that saw nothing for a column
+        pack[0, off_sum + 3] = 0.0
+    Mr, Lr = pack[:, off_ref:off_ref + B].double(), pack[:, off_sum:off_sum + B].double()
+    want = torch.logsumexp(Mr * math.log(2.0) + torch.log(Lr), dim=0)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    got = be.lse2_fold_ranks(pack, n_loc, n_loc, off_ref, off_sum, flag)
+    assert (got.double() - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+    flag.fill_(1)
+    got = be.lse2_fold_ranks(pack, n_loc, n_loc, off_ref, off_sum, flag)
+    assert torch.equal(got, pack[:, n_loc:2 * n_loc].reshape(-1))
