@@ -14,7 +14,6 @@ all-gather of the [B, D] operands and of the 2 B LSE values, all-reduce of scala
 No gradient reduce-scatter is needed: each rank recomputes its own row block of S for dI and
 its own column block for dT.
 """
-import math
 
 import torch
 import torch.distributed as dist

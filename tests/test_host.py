@@ -2,7 +2,6 @@
 and the sharded (world_size 2, gloo) algebra of losses.py against the oracle."""
 import ctypes
 import os
-import sys
 
 import numpy as np
 import pytest

@@ -201,9 +201,166 @@ void run(int n_clusters, int reps, bool check) {
   cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dclk);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The data path of the planned pair kernel, one tile pair, K = 64:
+//   MMA1 (cta_group::2, transposed): St_c[j, i] = sum_k X_c[j, k] A[i, k]   -- M side = CTA c's own column tile X_c
+//        (128 rows, K-major), N side = the SHARED row block A, each CTA staging 64 of its 128 rows;
+//   epilogue: thread j reads St_c[j, 0..127] and writes W_c[i, j] = bf16(0.25 St_c[j, i]) as an MN-major SW128 tile
+//        (rows = K index j, 64 consecutive i per 128-byte row, two 64-wide i blocks 16 KB apart);
+//   MMA2 (cta_group::1): OUT_c[i, d] = sum_j W_c[i, j] X_c[j, d]   -- A = W_c with a_major = MN, B = the SAME X_c bytes
+//        read MN-major (rows = K index j, 64 d per row).
+__global__ void __launch_bounds__(128, 1) k_chain(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ X,
+                                                   float* __restrict__ St, float* __restrict__ OUT) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;                  // [128 j][64] 16 KB
+  uint8_t* sA = smem + 16384;          // [64 i][64]   8 KB (this CTA's half of the row block)
+  uint8_t* sW = smem + 32768;          // 2 x [128 j][64 i] 32 KB, MN-major
+  __shared__ __align__(8) uint64_t bar1, bar2;
+  __shared__ uint32_t tmem_base;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = cluster_ctarank();
+  for (int e = tid; e < 128 * 64; e += 128) {
+    int r = e >> 6, k = e & 63;
+    *(__nv_bfloat16*)(sX + sw128_off(r, k)) = X[(size_t)(crank * 128 + r) * 64 + k];
+  }
+  for (int e = tid; e < 64 * 64; e += 128) {
+    int r = e >> 6, k = e & 63;
+    *(__nv_bfloat16*)(sA + sw128_off(r, k)) = A[(size_t)(crank * 64 + r) * 64 + k];
+  }
+  if (tid == 0) {
+    ptx::mbar_init(ptx::smem_u32(&bar1), 1);
+    ptx::mbar_init(ptx::smem_u32(&bar2), 1);
+    ptx::fence_barrier_init();
+  }
+  ptx::fence_proxy_async_smem();
+  cluster_sync_all();
+  if (warp == 0) tmem_alloc2(ptx::smem_u32(&tmem_base), 256);
+  ptx::tc_fence_before();
+  cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  if (warp == 1 && crank == 0) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::idesc_f16(256, 128, 1, 1, 0, 0);
+      const uint64_t ad = ptx::desc_kmajor(ptx::smem_u32(sX)), bd = ptx::desc_kmajor(ptx::smem_u32(sA));
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_ss2(tm, ad + 2 * kk, bd + 2 * kk, idesc, kk != 0);
+      umma_commit2(ptx::smem_u32(&bar1));
+    }
+    __syncwarp();
+  }
+  ptx::mbar_wait(ptx::smem_u32(&bar1), 0, 1);
+  ptx::tc_fence_after();
+  const int j = warp * 32 + lane;
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) St[((size_t)crank * 128 + j) * 128 + c0 + c] = __uint_as_float(v[c]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i0 = c0 + 8 * q;
+      uint32_t w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        w[u] = ptx::pack_bf16(0.25f * __uint_as_float(v[8 * q + 2 * u]), 0.25f * __uint_as_float(v[8 * q + 2 * u + 1]));
+      const uint32_t addr = ptx::smem_u32(sW) + (uint32_t)((i0 >> 6) * 16384 + (j >> 3) * 1024 + (j & 7) * 128 +
+                                                           ((((i0 & 63) >> 3) ^ (j & 7)) << 4));
+      ptx::st_shared_v4(addr, w[0], w[1], w[2], w[3]);
+    }
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::idesc_f16(128, 64, 1, 1, 1, 1);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t ad = ptx::desc_mnmajor(ptx::smem_u32(sW) + 2048u * ks, 16384);
+        const uint64_t bd = ptx::desc_mnmajor(ptx::smem_u32(sX) + 2048u * ks, 16384);
+        ptx::umma_ss(tm + 128, ad, bd, idesc, ks != 0);
+      }
+      ptx::umma_commit(ptx::smem_u32(&bar2));
+    }
+    __syncwarp();
+  }
+  ptx::mbar_wait(ptx::smem_u32(&bar2), 0, 2);
+  ptx::tc_fence_after();
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + 128 + c0, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) OUT[((size_t)crank * 128 + j) * 64 + c0 + c] = __uint_as_float(v[c]);
+  }
+  ptx::tc_fence_before();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc2(tm, 256);
+}
+
+void run_chain() {
+  std::vector<__nv_bfloat16> hA(128 * 64), hX(256 * 64);
+  std::vector<float> fA(hA.size()), fX(hX.size());
+  srand(77);
+  for (size_t i = 0; i < hA.size(); ++i) { hA[i] = __float2bfloat16((rand() % 2001 - 1000) / 1000.0f); fA[i] = __bfloat162float(hA[i]); }
+  for (size_t i = 0; i < hX.size(); ++i) { hX[i] = __float2bfloat16((rand() % 2001 - 1000) / 1000.0f); fX[i] = __bfloat162float(hX[i]); }
+  __nv_bfloat16 *dA, *dX;
+  float *dSt, *dOut;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dX, hX.size() * 2));
+  CK(cudaMalloc(&dSt, 2 * 128 * 128 * 4));
+  CK(cudaMalloc(&dOut, 2 * 128 * 64 * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  const size_t smem = 1024 + 65536;
+  CK(cudaFuncSetAttribute(k_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const __nv_bfloat16 *cA = dA, *cX = dX;
+  CK(cudaLaunchKernelEx(&cfg, k_chain, cA, cX, dSt, dOut));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hSt(2 * 128 * 128), hOut(2 * 128 * 64);
+  CK(cudaMemcpy(hSt.data(), dSt, hSt.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hOut.data(), dOut, hOut.size() * 4, cudaMemcpyDeviceToHost));
+  double e1 = 0.0, e2 = 0.0, mag = 0.0;
+  std::vector<float> W(128 * 128);
+  for (int c = 0; c < 2; ++c) {
+    for (int j = 0; j < 128; ++j)
+      for (int i = 0; i < 128; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < 64; ++k) acc += (double)fX[((size_t)c * 128 + j) * 64 + k] * fA[(size_t)i * 64 + k];
+        e1 = fmax(e1, fabs(acc - hSt[((size_t)c * 128 + j) * 128 + i]));
+        W[(size_t)i * 128 + j] = __bfloat162float(__float2bfloat16(0.25f * hSt[((size_t)c * 128 + j) * 128 + i]));
+      }
+    for (int i = 0; i < 128; ++i)
+      for (int d = 0; d < 64; ++d) {
+        double acc = 0.0;
+        for (int j = 0; j < 128; ++j) acc += (double)W[(size_t)i * 128 + j] * fX[((size_t)c * 128 + j) * 64 + d];
+        e2 = fmax(e2, fabs(acc - hOut[((size_t)c * 128 + i) * 64 + d]));
+        mag = fmax(mag, fabs(acc));
+      }
+  }
+  printf("chain: transposed cta_group::2 MMA1 max|err| %.3g; MN-major W -> MMA2 max|err| %.3g (max |OUT| %.3g)\n", e1, e2, mag);
+  cudaFree(dA); cudaFree(dX); cudaFree(dSt); cudaFree(dOut);
+}
+
 }  // namespace
 
 int main() {
+  run_chain();
   run<1, 128>(1, 1, true);
   run<1, 256>(1, 1, true);
   run<2, 128>(1, 1, true);

@@ -2,7 +2,6 @@
 deadlocks on the CPU before spending GPU time.  Each role is a generator that yields ("wait", barrier, parity)
 or ("arrive", barrier) / ("commit", barrier) steps; commits complete only after every earlier MMA of the same
 issuer has "executed" (the tensor pipe is modelled as a FIFO that retires ops whose operands are ready)."""
-import itertools
 import sys
 
 
