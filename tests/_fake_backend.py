@@ -45,6 +45,15 @@ class FakeBackend:
         dm = (dC - c * (c * dC).sum(1, keepdim=True)) * inv[:, None] * 0.5 * host_scale
         return dm, (dm.clone() if both else None)
 
+    def normalize_fwd(self, x, out_dtype):
+        inv = 1.0 / x.norm(dim=1)                                # no eps, as sparsify_clip.py:772-773
+        return (x * inv[:, None]).to(out_dtype), inv
+
+    def normalize_bwd(self, x, dY, inv):
+        y = x * inv[:, None]
+        dY = dY.to(x.dtype)
+        return (dY - y * (y * dY).sum(1, keepdim=True)) * inv[:, None]
+
     def lse2_fold_ranks(self, pack_all, n_loc, off_exact, off_ref, off_sum, flag):
         B = pack_all.shape[0] * n_loc
         if int(flag.item()) != 0:
