@@ -106,3 +106,34 @@ def test_sharded_step_equals_full_batch_step():
         num = sum((a - b.grad).pow(2).sum().item() for a, b in zip(grads, model.parameters()))
         den = sum(b.grad.pow(2).sum().item() for b in model.parameters())
         assert math.sqrt(num / den) <= 1e-4, (r, math.sqrt(num / den))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("amp", [None, torch.bfloat16, torch.float16])
+def test_train_step_on_gpu_matches_eager_reference_arithmetic(amp):
+    """The c5 caller on the real library: first-step loss of both experiment-6 phases against the reference's op
+    sequence in eager PyTorch on the same towers, and a parameter update that stays finite."""
+    import torch.nn.functional as F
+    cfg = dict(CFG, fp16=False)
+    images, tokens = _data(96, 5)
+    images, tokens = images.cuda(), tokens.cuda()
+    for epoch in (0, 1):
+        torch.manual_seed(0)
+        model = MiniCLIP(**TINY).cuda()
+        ts = TrainStep(model, cfg, t_total=10, amp_dtype=amp, steps_sparsify=0)
+        with torch.no_grad(), torch.autocast("cuda", dtype=amp, enabled=amp is not None):
+            i, t = model.encode_image(images).float(), model.encode_text(tokens).float()
+        i, t = F.normalize(i, dim=-1), F.normalize(t, dim=-1)
+        lunif = lambda x: torch.pdist(x).pow(2).mul(-2).exp().mean().log()
+        if epoch == 0:
+            want = 0.5 * (lunif(i) + lunif(t))
+        else:
+            logits = i @ t.t() / 0.1
+            tgt = torch.arange(96, device="cuda")
+            want = (0.5 * (F.cross_entropy(logits, tgt) + F.cross_entropy(logits.t(), tgt)) + (i - t).norm(dim=1).pow(2).mean()
+                    + lunif(F.normalize((i + t) / 2, dim=-1)))
+        got = ts(images, tokens, epoch=epoch)
+        tol = 1e-4 if amp is None else 3e-2          # autocast rounds the embeddings to 8 / 11 bits before the loss
+        assert abs(got.item() - want.item()) <= tol * max(1.0, abs(want.item())), (amp, epoch, got.item(), want.item())
+        assert all(torch.isfinite(p).all() for p in model.parameters())
+        assert ts.temperature.grad is None or torch.isfinite(ts.temperature.grad).all()
