@@ -77,6 +77,20 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -1
     with pytest.raises(ValueError):
         _lib.check(rc, "lse_pass")
+    # the packed-gather fold: offsets must lie inside one packed row (non-null dummy pointers; nothing is launched)
+    buf = (ctypes.c_float * 4)()
+    flag = (ctypes.c_int * 1)()
+    p, f = ctypes.addressof(buf), ctypes.addressof(flag)
+    assert lib.scb_lse2_fold_ranks(p, 2, 100, 10, 10, 25, 90, f, p, None) == -1      # sums run past the row
+    assert b"offsets" in lib.scb_last_error()
+    assert lib.scb_lse2_fold_ranks(p, 0, 100, 10, 10, 25, 45, f, p, None) == -1      # world = 0
+    assert lib.scb_lse2_fold_ranks(p, 2, 100, 0, 0, 0, 0, f, p, None) == 0           # nothing to do
+    # the fused combine: a term's inputs must come together, the output layout must hold a row
+    assert lib.scb_grad_combine(p, None, 4, 8, 8, 8, _lib.SCB_BF16, p, 1, None, None, None, 1.0, 1.0, None, 0, None, 0, 0.0,
+                                None, 0.0, None, 0.0, None, p, _lib.SCB_BF16, 8, None) == -1
+    assert b"anchor" in lib.scb_last_error()
+    assert lib.scb_grad_combine(p, p, 4, 8, 8, 8, _lib.SCB_BF16, None, 0, None, None, None, 1.0, 1.0, None, 0, None, 0, 0.0,
+                                None, 1.0, None, 0.0, None, p, _lib.SCB_BF16, 4, None) == -1
 
 
 def test_no_cpu_fallback():
