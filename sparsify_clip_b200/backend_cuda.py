@@ -82,6 +82,33 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+# Host-side cost matters for small batches (a B=4096 step is ~0.45 ms of GPU time and ~50 launches): the public
+# torch.cuda.device() / current_stream() helpers cost several microseconds per call, their C accessors a fraction of one.
+_get_device = torch._C._cuda_getDevice
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+class _On:
+    """`with _On(dev)` that does nothing when `dev` is already current (the usual case)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        self.idx = dev.index
+
+    def __enter__(self):
+        self.prev = _get_device()
+        if self.idx is None:
+            self.idx = self.prev
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev != self.idx:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 class CudaBackend:
     name = "cuda"
 
@@ -89,6 +116,7 @@ class CudaBackend:
         self.lib = _lib.load()
         self.launches = 0          # kernels launched through this backend (bench.py reports it)
         self.pass_events = None    # when a list: (name, start_event, end_event) per B x B pass
+        self._sm_count = {}
 
     def _count(self, n=1):
         self.launches += n
@@ -141,10 +169,17 @@ class CudaBackend:
 
     @staticmethod
     def _stream():
+        """The caller's stream on the current device (every use sits inside `with _On(device)`)."""
+        if _raw_stream is not None:
+            return _raw_stream(_get_device())
         return torch.cuda.current_stream().cuda_stream
 
     def _n_sm(self, dev):
-        return torch.cuda.get_device_properties(dev).multi_processor_count
+        idx = dev.index if dev.index is not None else _get_device()
+        n = self._sm_count.get(idx)
+        if n is None:
+            n = self._sm_count[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+        return n
 
     def _plan(self, path, nA, nB, D, grad, dev):
         """(jparts, nsub) of one B x B pass, from the library's planner."""
@@ -157,7 +192,7 @@ class CudaBackend:
         x = x.contiguous().view(-1)
         out = _empty((), dtype=torch.float32, device=x.device)
         scratch = _empty(1024, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _On(x.device):
             check(self.lib.scb_sum(_ptr(x), x.numel(), _ptr(scratch), _ptr(out), self._stream()), "sum")
         self._count(2)
         return out
@@ -165,7 +200,7 @@ class CudaBackend:
     # ------------------------------------------------------------------ row-wise
     def row_sqnorm(self, x):
         out = _empty(x.shape[0], dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _On(x.device):
             check(self.lib.scb_row_sqnorm(_ptr(x), x.shape[0], x.shape[1], x.stride(0), _DT[x.dtype], _ptr(out),
                                           self._stream()), "row_sqnorm")
         self._count()
@@ -173,7 +208,7 @@ class CudaBackend:
 
     def row_dot(self, a, b):
         out = _empty(a.shape[0], dtype=torch.float32, device=a.device)
-        with torch.cuda.device(a.device):
+        with _On(a.device):
             check(self.lib.scb_row_dot(_ptr(a), _ptr(b), a.shape[0], a.shape[1], a.stride(0), b.stride(0), _DT[a.dtype],
                                        _ptr(out), self._stream()), "row_dot")
         self._count()
@@ -181,7 +216,7 @@ class CudaBackend:
 
     def lalign_rows(self, x, y):
         out = _empty(x.shape[0], dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _On(x.device):
             check(self.lib.scb_lalign_rows(_ptr(x), _ptr(y), x.shape[0], x.shape[1], x.stride(0), y.stride(0),
                                            _DT[x.dtype], _ptr(out), self._stream()), "lalign_rows")
         self._count()
@@ -191,7 +226,7 @@ class CudaBackend:
         n, D = x.shape
         dX = _empty(n, D, dtype=torch.float32, device=x.device) if want_x else None
         dY = _empty(n, D, dtype=torch.float32, device=x.device) if want_y else None
-        with torch.cuda.device(x.device):
+        with _On(x.device):
             check(self.lib.scb_lalign_bwd(_ptr(x), _ptr(y), n, D, x.stride(0), y.stride(0), _DT[x.dtype], host_scale,
                                           _ptr(dev_scale), 0, _ptr(dX), _ptr(dY), self._stream()), "lalign_bwd")
         self._count()
@@ -201,7 +236,7 @@ class CudaBackend:
         n, D = a.shape
         C = _empty(n, D, dtype=out_dtype, device=a.device)
         inv = _empty(n, dtype=torch.float32, device=a.device)
-        with torch.cuda.device(a.device):
+        with _On(a.device):
             check(self.lib.scb_centroid_fwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(C),
                                             _DT[out_dtype], _ptr(inv), self._stream()), "centroid_fwd")
         self._count()
@@ -212,7 +247,7 @@ class CudaBackend:
         n, D = a.shape
         dA = _empty(n, D, dtype=torch.float32, device=a.device)
         dB = _empty(n, D, dtype=torch.float32, device=a.device) if both else None
-        with torch.cuda.device(a.device):
+        with _On(a.device):
             check(self.lib.scb_centroid_bwd(_ptr(a), _ptr(b), n, D, a.stride(0), b.stride(0), _DT[a.dtype], _ptr(dC),
                                             _ptr(inv), host_scale, _ptr(dev_scale), 0, _ptr(dA), _ptr(dB),
                                             self._stream()), "centroid_bwd")
@@ -223,7 +258,7 @@ class CudaBackend:
         n, D = x.shape
         Y = _empty(n, D, dtype=out_dtype, device=x.device)
         inv = _empty(n, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _On(x.device):
             check(self.lib.scb_normalize_fwd(_ptr(x), n, D, x.stride(0), _DT[x.dtype], _ptr(Y), _DT[out_dtype],
                                              _ptr(inv), self._stream()), "normalize_fwd")
         self._count()
@@ -232,7 +267,7 @@ class CudaBackend:
     def normalize_bwd(self, x, dY, inv):
         n, D = x.shape
         dX = _empty(n, D, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _On(x.device):
             check(self.lib.scb_normalize_bwd(_ptr(x), n, D, x.stride(0), _DT[x.dtype], _ptr(dY), _ptr(inv), _ptr(dX),
                                              self._stream()), "normalize_bwd")
         self._count()
@@ -248,7 +283,7 @@ class CudaBackend:
         pm = _empty(jp * nsub, nA, dtype=torch.float32, device=A.device)
         pl = torch.empty_like(pm)
         out = _empty(nA, dtype=torch.float32, device=A.device)
-        with torch.cuda.device(A.device):
+        with _On(A.device):
             with self._Timed(self, "lse"):
                 check(self.lib.scb_lse_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0), _DT[A.dtype],
                                             float(scale), jp, _ptr(pm), _ptr(pl), path, self._stream()), "lse_pass")
@@ -278,7 +313,7 @@ class CudaBackend:
         pm2, pl2 = _empty(jp2 * nsub2, nB, **f32), _empty(jp2 * nsub2, nB, **f32)
         sqa, sqb = self.row_sqnorm(A), self.row_sqnorm(Bm)
         st = self._stream()
-        with torch.cuda.device(dev):
+        with _On(dev):
             check(self.lib.scb_lse2_spread_flag(_ptr(sqa), nA, _ptr(sqb), nB, float(scale), _ptr(flag), st), "lse2_spread_flag")
             with self._Timed(self, "lse"):
                 check(self.lib.scb_lse2_pass(_ptr(A), nA, _ptr(Bm), nB, D, A.stride(0), Bm.stride(0), _DT[A.dtype],
@@ -319,7 +354,7 @@ class CudaBackend:
         pm2, pl2 = _empty(jp2 * nsub2, nR, **f32), _empty(jp2 * nsub2, nR, **f32)
         sqa, sqb = self.row_sqnorm(A_all), self.row_sqnorm(Bm_all)
         st = self._stream()
-        with torch.cuda.device(dev):
+        with _On(dev):
             check(self.lib.scb_lse2_spread_flag(_ptr(sqa), A_all.shape[0], _ptr(sqb), nB, float(scale), _ptr(flag), st),
                   "lse2_spread_flag")
             with self._Timed(self, "lse"):
@@ -342,7 +377,7 @@ class CudaBackend:
         ws, width = pack_all.shape
         assert pack_all.dtype == torch.float32 and pack_all.is_contiguous()
         out = _empty(ws * n_loc, dtype=torch.float32, device=pack_all.device)
-        with torch.cuda.device(pack_all.device):
+        with _On(pack_all.device):
             check(self.lib.scb_lse2_fold_ranks(_ptr(pack_all), ws, width, n_loc, off_exact, off_ref, off_sum, _ptr(flag),
                                                _ptr(out), self._stream()), "lse2_fold_ranks")
         self._count()
@@ -359,7 +394,7 @@ class CudaBackend:
         out = _empty(jp, nA, D, dtype=torch.float32, device=A.device)
         ws = _empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
         dA = _empty(nA, D, dtype=torch.float32, device=A.device)
-        with torch.cuda.device(A.device):
+        with _On(A.device):
             with self._Timed(self, "anchor_grad"):
                 check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0),
                                                     _DT[A.dtype], float(scale), _ptr(row_lse), _ptr(col_lse_all),
@@ -380,7 +415,7 @@ class CudaBackend:
         jp, nsub = self._plan(path, nA, nB, D, True, A.device)
         out = _empty(jp, nA, D, dtype=torch.float32, device=A.device)
         ws = _empty(jp * nsub, nA, dtype=torch.float32, device=A.device) if want_ws else None
-        with torch.cuda.device(A.device):
+        with _On(A.device):
             with self._Timed(self, "anchor_grad"):
                 check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0),
                                                     _DT[A.dtype], float(scale), _ptr(row_lse), _ptr(col_lse_all),
@@ -399,7 +434,7 @@ class CudaBackend:
         dX = _empty(n, D, dtype=out_dtype, device=X.device)
         a, u = anchor or {}, unif or {}
         core = u.get("core") or {}
-        with torch.cuda.device(X.device):
+        with _On(X.device):
             check(self.lib.scb_grad_combine(
                 _ptr(X), _ptr(Y), n, D, X.stride(0), Y.stride(0) if Y is not None else 0, _DT[X.dtype],
                 _ptr(a.get("out")), int(a.get("jparts", 0)), _ptr(a.get("row_lse")), _ptr(a.get("col_lse_rows")),
@@ -423,7 +458,7 @@ class CudaBackend:
             sqn_r = sqn_all[row_offset:row_offset + nR]
         rs = _empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
         core = {"jparts": jp, "nparts": jp * nsub, "path": path}
-        with torch.cuda.device(Xr.device):
+        with _On(Xr.device):
             if need_grad:
                 U = _empty(jp, nR, D, dtype=torch.float32, device=Xr.device)
                 rq = _empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
@@ -445,7 +480,7 @@ class CudaBackend:
         """dX = s * (rq_i x_i - U_i), s = host_scale * dev_scale (0-dim device tensor)."""
         nR, D = Xr.shape
         dX = _empty(nR, D, dtype=torch.float32, device=Xr.device)
-        with torch.cuda.device(Xr.device):
+        with _On(Xr.device):
             check(self.lib.scb_lunif_grad_finalize(_ptr(core["U"]), core["jparts"], _ptr(core["rq"]), core["nparts"], nR, D,
                                                    _ptr(Xr), Xr.stride(0), _DT[Xr.dtype], float(host_scale), _ptr(dev_scale),
                                                    0, _ptr(dX), self._stream()), "lunif_grad_finalize")
@@ -458,7 +493,7 @@ class CudaBackend:
         path = self.path_for(Xr, Xall)
         jp, nsub = self._plan(path, nR, nAll, D, False, Xr.device)
         rs = _empty(jp * nsub, nR, dtype=torch.float32, device=Xr.device)
-        with torch.cuda.device(Xr.device):
+        with _On(Xr.device):
             check(self.lib.scb_sparsify_sum_pass(_ptr(Xr), nR, _ptr(Xall), nAll, D, Xr.stride(0), Xall.stride(0),
                                                  _DT[Xr.dtype], int(row_offset), jp, _ptr(rs), path, self._stream()),
                   "sparsify_sum_pass")
