@@ -190,6 +190,15 @@ int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, int64_t ldX
                      const float* extra, float e_coef, const float* dev_scale, void* dX, int out_dtype,
                      int64_t ldOut, void* stream);
 
+/* Scalar assembly of the composed loss (the additions of the ladder, sparsify_clip.py:778-938, on the partial sums):
+ * parts = [sum_i row_lse, sum_j col_lse, sum_i I_i.T_i, sum_i |I_i - T_i|^2, rs(img), rs(txt), rs(cen)] (device),
+ *   *loss = c_anchor (parts[0] + parts[1] - two_scale parts[2]) + c_align parts[3]
+ *           + sum_k w_k log( (parts[4+k] / 2) / pair_norm ),      inv_ssum[k] = 2 / parts[4+k]   (0 when w_k == 0)
+ * c_anchor = w_anchor / 2B, two_scale = 2 / tau, c_align = w_align / B, pair_norm = B (B - 1) / 2; a zero weight
+ * skips its term.  One launch instead of ~20 one-element element-wise launches of the host framework. */
+int scb_loss_assemble(const float* parts, float c_anchor, float two_scale, float c_align, float w_unif_img,
+                      float w_unif_txt, float w_unif_cen, float pair_norm, float* loss, float* inv_ssum, void* stream);
+
 /* sparsify_loss (sparsify_clip.py:166-176), forward: row partial sums of
  * (x_i.x_j - (2 delta_ij - 1))^2 over j; rs [jparts*nsub][nR]. */
 int scb_sparsify_sum_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,

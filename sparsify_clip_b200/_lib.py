@@ -44,6 +44,7 @@ SIGNATURES = {
     "scb_lunif_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _i32, _vp],
     "scb_lunif_grad_finalize": [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _i64, _i32, _f32, _vp, _i32, _vp, _vp],
     "scb_debug_pair_trace": [_vp],
+    "scb_loss_assemble": [_vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
     "scb_lse2_fold_ranks": [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp],
     "scb_grad_combine": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i32, _vp, _i32,
                          _f32, _vp, _f32, _vp, _f32, _vp, _vp, _i32, _i64, _vp],

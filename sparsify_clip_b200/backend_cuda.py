@@ -188,9 +188,11 @@ class CudaBackend:
                                      ctypes.byref(nsub)), "pass_plan")
         return jp.value, nsub.value
 
-    def sum(self, x):
+    def sum(self, x, out=None):
+        """Deterministic sum of all elements -> 0-dim fp32 (or written into `out`, a one-element fp32 view)."""
         x = x.contiguous().view(-1)
-        out = _empty((), dtype=torch.float32, device=x.device)
+        if out is None:
+            out = _empty((), dtype=torch.float32, device=x.device)
         scratch = _empty(1024, dtype=torch.float32, device=x.device)
         with _On(x.device):
             check(self.lib.scb_sum(_ptr(x), x.numel(), _ptr(scratch), _ptr(out), self._stream()), "sum")
@@ -445,7 +447,18 @@ class CudaBackend:
         self._count()
         return dX
 
-    def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None):
+    def loss_assemble(self, parts, c_anchor, two_scale, c_align, w_img, w_txt, w_cen, pair_norm):
+        """(loss 0-dim, inv_ssum [3]) from the partial sums (scb_loss_assemble)."""
+        loss = _empty((), dtype=torch.float32, device=parts.device)
+        inv = _empty(3, dtype=torch.float32, device=parts.device)
+        with _On(parts.device):
+            check(self.lib.scb_loss_assemble(_ptr(parts), float(c_anchor), float(two_scale), float(c_align), float(w_img),
+                                             float(w_txt), float(w_cen), float(pair_norm), _ptr(loss), _ptr(inv),
+                                             self._stream()), "loss_assemble")
+        self._count()
+        return loss, inv
+
+    def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None, sum_out=None):
         """One sweep over the pairwise Gaussian potentials of the rows of Xr against Xall.
         Returns {'rs_sum': 0-dim sum_i sum_{j != i} w_ij, and, when need_grad, 'U', 'rq', ...}."""
         nR, D = Xr.shape
@@ -473,7 +486,7 @@ class CudaBackend:
                                                   _DT[Xr.dtype], float(t), _ptr(sqn_r), _ptr(sqn_all), int(row_offset), jp,
                                                   _ptr(rs), path, self._stream()), "lunif_sum_pass")
                 self._count()
-        core["rs_sum"] = self.sum(rs)
+        core["rs_sum"] = self.sum(rs, out=sum_out)
         return core
 
     def lunif_grad(self, core, Xr, host_scale, dev_scale):

@@ -275,6 +275,26 @@ __global__ void __launch_bounds__(256) k_colstat_fold(const float* __restrict__ 
   }
 }
 
+// Scalar assembly of the composed loss from the step's partial sums (one thread; replaces ~20 one-element
+// element-wise launches of the host framework per step).  p = [sum r, sum c, sum diag, sum |x-y|^2, rsI, rsT, rsC].
+__global__ void k_loss_assemble(const float* __restrict__ p, float ca, float two_scale, float cl, float wi, float wt, float wc,
+                                float pair_norm, float* __restrict__ loss, float* __restrict__ inv_ssum) {
+  float L = 0.f;
+  if (ca != 0.f) L += ca * (p[0] + p[1] - two_scale * p[2]);
+  if (cl != 0.f) L += cl * p[3];
+  const float w[3] = {wi, wt, wc};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    inv_ssum[k] = 0.f;
+    if (w[k] != 0.f) {
+      const float ss = 0.5f * p[4 + k];
+      L += w[k] * logf(ss / pair_norm);          // B == 1: log(0 / 0) = nan, as the reference
+      inv_ssum[k] = 1.f / ss;
+    }
+  }
+  *loss = L;
+}
+
 // Fold of the per-rank column partials after the packed gather of a sharded step.  pack = [world][stride] fp32, one row
 // per rank: at off_exact the exact column LSE of that rank's own n_loc columns (valid when *flag != 0), at off_ref /
 // off_sum that rank's (reference, sum) partial of every one of the world * n_loc columns (log2 domain).
@@ -684,6 +704,16 @@ extern "C" int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* 
   SCB_CHECK_ARG(sqnA && sqnB && flag && nA >= 0 && nB >= 0 && scale > 0.f, SCB_E_ARG, "lse2_spread_flag: bad argument");
   k_spread_flag<<<1, 1024, 0, (cudaStream_t)stream>>>(sqnA, nA, sqnB, nB, scale, 90.f, flag);
   SCB_CHECK_LAUNCH("lse2_spread_flag");
+  return 0;
+}
+
+extern "C" int scb_loss_assemble(const float* parts, float c_anchor, float two_scale, float c_align, float w_unif_img,
+                                 float w_unif_txt, float w_unif_cen, float pair_norm, float* loss, float* inv_ssum,
+                                 void* stream) {
+  SCB_CHECK_ARG(parts && loss && inv_ssum, SCB_E_ARG, "loss_assemble: bad argument");
+  k_loss_assemble<<<1, 1, 0, (cudaStream_t)stream>>>(parts, c_anchor, two_scale, c_align, w_unif_img, w_unif_txt, w_unif_cen,
+                                                     pair_norm, loss, inv_ssum);
+  SCB_CHECK_LAUNCH("loss_assemble");
   return 0;
 }
 

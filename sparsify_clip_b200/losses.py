@@ -223,13 +223,12 @@ class _FusedTermsFn(torch.autograd.Function):
             if w_c != 0.0:
                 C_all, h = _all_gather_rows_async(Cq, group)
                 pending.append(h)
-        # scalar partial sums of this rank
-        #   0: anchor (sum r + sum c - 2/tau sum diag)   1: L_align   2, 3, 4: L_unif row sums (I, T, centroids)
-        #   5: d/dtau
-        NS = 5                                               # how many of them travel in the packed gather
+        # scalar partial sums of this rank, written in place by the kernels that produce them:
+        #   0: sum r   1: sum c   2: sum diag   3: L_align   4, 5, 6: L_unif row sums (I, T, centroids)   7: d/dtau
+        NS = 7                                               # how many of them travel in the packed gather
         parts = torch.zeros(NS + 1, dtype=torch.float32, device=dev)
         if w_l != 0.0:
-            parts[1] = be.sum(be.lalign_rows(Ip, Tp))
+            be.sum(be.lalign_rows(Ip, Tp), out=parts[3:4])
         for h in pending:
             h.wait()
         an_I = an_T = None
@@ -250,19 +249,18 @@ class _FusedTermsFn(torch.autograd.Function):
                 else:                                       # one sweep: my rows of S; the column sums are folded
                     r = colparts[0]                         # over the ranks after the gather below
             diag = be.row_dot(Ip, Tp)
-            sdiag = be.sum(diag)
-            parts[0] = be.sum(r) - (2.0 * scale) * sdiag
+            be.sum(r, out=parts[0:1])
+            be.sum(diag, out=parts[2:3])
             if colparts is None:
-                parts[0] = parts[0] + be.sum(c)
+                be.sum(c, out=parts[1:2])
         un_I = un_T = None
         cores = {}
-        for (wu, Xp, X_all, needx, which, slot) in ((w_i, Ip, I_all, need_I, "I", 2), (w_t, Tp, T_all, need_T, "T", 3),
-                                                    (w_c, Cq, C_all, need, "C", 4)):
+        for (wu, Xp, X_all, needx, which, slot) in ((w_i, Ip, I_all, need_I, "I", 4), (w_t, Tp, T_all, need_T, "T", 5),
+                                                    (w_c, Cq, C_all, need, "C", 6)):
             if wu == 0.0:
                 continue
-            core = be.lunif_core(Xp, X_all, float(t_unif), off, needx)
-            parts[slot] = core["rs_sum"]
-            cores[which] = (core, wu, needx)
+            core = be.lunif_core(Xp, X_all, float(t_unif), off, needx, sum_out=parts[slot:slot + 1])
+            cores[which] = (core, wu, needx, slot - 4)
         # ---- exchange step 2: ONE small gather carries r, c and the scalar partials of every rank.  It is issued
         # between sweeps, not under one: an NCCL kernel that shares the SMs with a persistent sweep slows the sweep
         # more than the overlap saves (measured at 8 GPUs).
@@ -279,6 +277,7 @@ class _FusedTermsFn(torch.autograd.Function):
             dist.all_gather_into_tensor(pack_flat, pack, group=group)
             pack_all = pack_flat.view(ws, -1)
             r_all = pack_all[:, :n].reshape(-1)
+            local_sdiag = parts[2].clone() if need_tau else None
             parts = torch.cat((pack_all[:, 2 * n:2 * n + NS].sum(0), parts[NS:]))
             if colparts is None:
                 c_all = pack_all[:, n:2 * n].reshape(-1)
@@ -286,15 +285,17 @@ class _FusedTermsFn(torch.autograd.Function):
                 # fold the column partials of all ranks (or take the exact second sweep where the bound demanded it)
                 c_all = be.lse2_fold_ranks(pack_all, n, n, 2 * n + NS, 2 * n + NS + B, flag)
                 c = c_all[off:off + n]
-                parts[0] = parts[0] + c_all.sum()
+                be.sum(c_all, out=parts[1:2])
             gathered = True
+        else:
+            local_sdiag = parts[2]
         if w_a != 0.0 and (need or need_tau):
             coef = w_a * scale / (2.0 * B)
             if need_I or need_tau:
                 p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
                 an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef)
                 if need_tau:
-                    parts[NS] = p["ws"] - 2.0 * sdiag
+                    parts[NS] = p["ws"] - 2.0 * local_sdiag
             if need_T:
                 p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
                 an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
@@ -304,13 +305,12 @@ class _FusedTermsFn(torch.autograd.Function):
                 _all_reduce_(parts, group)
             elif need_tau:
                 _all_reduce_(parts[NS:], group)
-        loss = (w_a / (2.0 * B)) * parts[0] + (w_l / B) * parts[1]
+        # the additions of the ladder on the (now global) partial sums, and 1 / Ssum of every L_unif term, in one launch
+        loss, inv_ssum = be.loss_assemble(parts, w_a / (2.0 * B), 2.0 * scale, w_l / B, w_i, w_t, w_c, B * (B - 1) / 2.0)
         cen = None
-        for which, (core, wu, needx) in cores.items():
-            ssum = parts[{"I": 2, "T": 3, "C": 4}[which]] * 0.5
-            loss = loss + wu * torch.log(ssum / (B * (B - 1) / 2.0))      # B == 1 -> nan, as the reference
+        for which, (core, wu, needx, k) in cores.items():
             if needx:
-                u = dict(core=core, coef=wu * (-2.0 * float(t_unif)), dev_coef=torch.reciprocal(ssum).reshape(1).contiguous())
+                u = dict(core=core, coef=wu * (-2.0 * float(t_unif)), dev_coef=inv_ssum[k:k + 1])
                 if which == "I":
                     un_I = u
                 elif which == "T":

@@ -18,8 +18,27 @@ class FakeBackend:
     def path_for(self, *mats):
         return 0
 
-    def sum(self, x):
-        return x.double().sum()
+    def sum(self, x, out=None):
+        v = x.double().sum()
+        if out is not None:
+            out.copy_(v.reshape(out.shape))
+            return out
+        return v
+
+    def loss_assemble(self, parts, c_anchor, two_scale, c_align, w_img, w_txt, w_cen, pair_norm):
+        p = parts.double()
+        loss = torch.zeros((), dtype=torch.float64)
+        if c_anchor != 0.0:
+            loss = loss + c_anchor * (p[0] + p[1] - two_scale * p[2])
+        if c_align != 0.0:
+            loss = loss + c_align * p[3]
+        inv = torch.zeros(3, dtype=torch.float64)
+        for k, w in enumerate((w_img, w_txt, w_cen)):
+            if w != 0.0:
+                ss = 0.5 * p[4 + k]
+                loss = loss + w * torch.log(ss / pair_norm)
+                inv[k] = 1.0 / ss
+        return loss, inv
 
     def row_sqnorm(self, x):
         return (x * x).sum(1)
@@ -117,7 +136,7 @@ class FakeBackend:
             g = g * dev_scale.double()
         return g.to(out_dtype)
 
-    def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None):
+    def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None, sum_out=None):
         n = (Xall * Xall).sum(1)
         nr = (Xr * Xr).sum(1)
         d2 = (nr[:, None] + n[None, :] - 2 * Xr @ Xall.t()).clamp_min(0)
@@ -125,6 +144,8 @@ class FakeBackend:
         idx = torch.arange(Xr.shape[0])
         W[idx, idx + row_offset] = 0
         core = {"rs_sum": W.sum()}
+        if sum_out is not None:
+            sum_out.copy_(core["rs_sum"].reshape(sum_out.shape))
         if need_grad:
             core.update(U=W @ Xall, rq=W.sum(1))
         return core
