@@ -239,3 +239,34 @@ def test_single_process_fake_backend_matches_oracle(fused):
     finally:
         scb.set_fused(pf)
         backend_cuda.set_backend(prev)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/scb200.h compiles as C99 and a C program linked against libscb200.so reaches the host-only entry points
+    (version, launch plan, argument validation) without Python or PyTorch in the process."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "sparsify_clip_b200")
+    _lib.load()                                              # builds the library if it is missing
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "scb200.h"
+int main(void) {
+  int jparts = 0, nsub = 0;
+  if (scb_pass_plan(SCB_PATH_TC, 32768, 32768, 512, 1, 148, &jparts, &nsub) != 0) return 2;
+  int rc = scb_row_sqnorm(NULL, 4, 8, 8, 7, NULL, NULL);
+  printf("%d %d %d %d %d\n", scb_version() > 0, jparts, nsub, rc, strstr(scb_last_error(), "dtype") != NULL);
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lscb200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    want_jp, want_nsub = _plan(_lib.PATH_TC, 32768, 32768, 512, 1)
+    assert out == ["1", str(want_jp), str(want_nsub), "-2", "1"], out
