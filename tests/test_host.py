@@ -270,3 +270,49 @@ int main(void) {
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     want_jp, want_nsub = _plan(_lib.PATH_TC, 32768, 32768, 512, 1)
     assert out == ["1", str(want_jp), str(want_nsub), "-2", "1"], out
+
+
+def _pair_segments(n_rb, n_jb, n_sm):
+    """Host mirror of the CTA-pair kernel's span walk (csrc/tc_pair.cu: SCB_PAIR_FOR_SEGMENTS / SCB_PAIR_ITEM_SETUP):
+    yields (pair, row block, first tile, tiles, partial slot)."""
+    pairs, span, pmax = scb.pair_span_plan(n_rb, n_jb, n_sm)
+    total = n_rb * n_jb
+    for pair in range(pairs):
+        g, g_end = pair * span, min(pair * span + span, total)
+        while g < g_end:
+            rb = g // n_jb
+            jb_lo = g - rb * n_jb
+            nt = min(n_jb - jb_lo, g_end - g)
+            jp = pair - (rb * n_jb) // span
+            yield pair, rb, jb_lo, nt, jp
+            g += nt
+    return pmax
+
+
+def test_pair_span_walk_covers_every_tile_once():
+    """Every (row block, column tile) belongs to exactly one segment, the partial slots of a row block are
+    0 .. k-1 with k <= the planner's slot count, and the C planner agrees with the mirror -- over many shard shapes."""
+    import random
+    rng = random.Random(5)
+    shapes = [(256, 256, 148), (32, 256, 148), (1, 1, 148), (3, 7, 148), (64, 512, 148), (2, 300, 148), (5, 33, 4)]
+    shapes += [(rng.randint(1, 80), rng.randint(1, 600), rng.choice([2, 8, 132, 148])) for _ in range(120)]
+    lib = _lib.load()
+    for n_rb, n_jb, n_sm in shapes:
+        pairs, span, pmax = scb.pair_span_plan(n_rb, n_jb, n_sm)
+        jp_c, nsub_c = ctypes.c_int(0), ctypes.c_int(0)
+        prev = lib.scb_set_tc_flags(3)
+        try:
+            assert lib.scb_pass_plan(_lib.PATH_TC, n_rb * 128, n_jb * 128, 512, 1, n_sm, ctypes.byref(jp_c), ctypes.byref(nsub_c)) == 0
+        finally:
+            lib.scb_set_tc_flags(prev)
+        assert (jp_c.value, nsub_c.value) == (pmax, 4), (n_rb, n_jb, n_sm)
+        assert pmax <= 16 and pairs <= max(1, n_sm // 2) and pairs * span >= n_rb * n_jb
+        seen = [[0] * n_jb for _ in range(n_rb)]
+        slots = [[] for _ in range(n_rb)]
+        for pair, rb, jb_lo, nt, jp in _pair_segments(n_rb, n_jb, n_sm):
+            assert nt >= 1 and 0 <= jp < pmax, (n_rb, n_jb, n_sm, pair, rb)
+            for j in range(jb_lo, jb_lo + nt):
+                seen[rb][j] += 1
+            slots[rb].append(jp)
+        assert all(v == 1 for row in seen for v in row), (n_rb, n_jb, n_sm)
+        assert all(s == list(range(len(s))) for s in slots), (n_rb, n_jb, n_sm)
