@@ -17,6 +17,7 @@ the reference op sequence (oracle/torch_port.py) on the host cores, on a bounded
 `--impl reference` times that CPU path alone and prints the same line shape.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -271,6 +272,12 @@ def run_ours(args):
     # One untimed back-to-back burst of the same length as the timed loop: with the CPU running ahead of the GPU several
     # steps' worth of buffers are alive at once, and the caching allocator must have grown to that peak BEFORE the timed
     # loop (a cudaMalloc inside it synchronises the device: measured as sporadic +30 % outliers).
+    # A third source, seen as ONE step of 64 ms (or +2 ms) right after a barrier, when the launch queue is empty and the
+    # host cannot hide anything: a full collection of the Python garbage collector over the import-time heap (torch,
+    # numpy, ...).  Collect now and freeze the survivors, so that collections inside the timed region only look at
+    # the objects the steps themselves create (what `timeit` achieves by switching the collector off).
+    gc.collect()
+    gc.freeze()
     for _ in range(args.steps):
         flush.zero_()
         step(I, T)
@@ -278,6 +285,7 @@ def run_ours(args):
 
     # ---- timed region: K steps, each bracketed by CUDA events, L2 flushed (untimed) in between
     first_row = len(sampler.rows)      # only samples taken from here on (the timed region) are reported
+    gc0 = [g["collections"] for g in gc.get_stats()]
     evs = []
     launches0 = be.launches
     barrier()
@@ -290,6 +298,7 @@ def run_ours(args):
         evs.append((e0, e1))
     barrier()
     launches = be.launches - launches0
+    gc_in_region = [g["collections"] - a for g, a in zip(gc.get_stats(), gc0)]
     # A short timed region yields too few nvidia-smi samples (100 ms period; denser polling was measured to stall the
     # GPU: outlier steps of 2x): keep the same load running, untimed, for ~0.6 s more.  Rank 0 owns the sampler and
     # decides; the step count is broadcast so that every rank runs the same collectives.
@@ -307,7 +316,8 @@ def run_ours(args):
         step(I, T)
         launches = (be.launches - l0) * args.steps
     clocks = sampler.stop(first_row) if rank == 0 else None
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    step_ms = [a.elapsed_time(b) for a, b in evs]          # this rank's per-step intervals (reported for transparency)
+    total_ms = sum(step_ms)
     tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -396,6 +406,8 @@ def run_ours(args):
                        "timing": "sum of per-step CUDA-event intervals, max over ranks",
                        "launch": "one CUDA-graph replay per step" if graphed is not None else "eager launches"},
             "loss": loss_val,
+            "step_ms_rank0": [round(x, 3) for x in step_ms],
+            "python_gc_collections_in_timed_region": gc_in_region,      # per generation, rank 0
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * D * 2, "d2h_bytes_per_step": 4,
                     "ms_per_step": et.item(),
                     "how": "public API on device buffers filled from pinned host memory; the copy of step k+1 overlaps "
