@@ -258,11 +258,13 @@ if __name__ == "__main__":
 
 
 def simulate_order(order="A", nt=128, nslots=6, lag_own=2, lag_peer=3, L_tma=1500.0, tma_bw=80.0, E=2300.0, X=3200.0,
-                   ack=400.0, chunk_clk=330.0, v_pair_clk=600.0, kch=8, gch=4, issue_cost=40.0, a_stream=2):
+                   ack=400.0, chunk_clk=330.0, v_pair_clk=600.0, kch=8, gch=4, issue_cost=40.0, a_stream=2, w_ring=False):
     """Like simulate() (single Wrecv, DSMEM hand-over) but the MMA/TMA issue order inside a step is a parameter:
     ops of the step of own tile t: MMA1 chunks c0..c7 of t, MMA2 groups o0,o1 of own tile t-lag_own, p0,p1 of peer tile
     t-lag_peer.  order: 'A' c0-7 o0 o1 p0 p1 (as built) | 'B' c0-3 o0 c4-7 o1 p0 p1 | 'C' c0-1 o0 c2-3 o1 c4-5 p0 c6-7 p1
-    | 'D' c0-3 o0 o1 c4-7 p0 p1."""
+    | 'D' c0-3 o0 o1 c4-7 p0 p1.
+    w_ring: no dedicated landing buffer -- the peer's weight tile lands in two ordinary ring slots that the receiver's
+    producer grants (in ring order) instead of filling them by TMA; they are released after the second MMA2-peer group."""
     sim = Sim()
     CH = 16384.0
     for c in (0, 1):
@@ -275,6 +277,8 @@ def simulate_order(order="A", nt=128, nslots=6, lag_own=2, lag_peer=3, L_tma=150
             sim.bar((c, "g_full", b), 1)
         sim.bar((c, "w_full", 0), 1)
         sim.bar((c, "w_empty", 0), 1)
+        sim.bar((c, "w_grant", 0), 2)
+    wslots = [dict(), dict()]
     pipe_free, pipe_busy, tma_free, end_time = [0.0, 0.0], [0.0, 0.0], [0.0, 0.0], [0.0, 0.0]
     pat = {"A": "c0 c1 c2 c3 c4 c5 c6 c7 o0 o1 p0 p1", "B": "c0 c1 c2 c3 o0 c4 c5 c6 c7 o1 p0 p1",
            "C": "c0 c1 o0 c2 c3 o1 c4 c5 p0 c6 c7 p1", "D": "c0 c1 c2 c3 o0 o1 c4 c5 c6 c7 p0 p1",
@@ -301,15 +305,22 @@ def simulate_order(order="A", nt=128, nslots=6, lag_own=2, lag_peer=3, L_tma=150
     def nslots_of(op):
         if op[0] == "c":
             return 2 if op[2] >= kch - a_stream else 1
+        if w_ring and op[0] == "p" and op[2] == 0:
+            return 4                                   # the weight tile's two slots, then the V pair
         return 2
 
     def producer(c):
         t = yield ("delay", 0)
         slot, uses = 0, defaultdict(int)
         for op in ops(c):
-            for _ in range(nslots_of(op)):
+            for i in range(nslots_of(op)):
                 t = yield ("wait", (c, "empty", slot), uses[slot] - 1)
                 uses[slot] += 1
+                if w_ring and op[0] == "p" and op[2] == 0 and i < 2:      # grant the slot to the peer's sender
+                    wslots[c].setdefault(op[1] // 2, []).append(slot)
+                    t = yield ("arrive", (c, "w_grant", 0), t + ack)
+                    slot = (slot + 1) % nslots
+                    continue
                 start = max(t + L_tma, tma_free[c])
                 tma_free[c] = start + CH / tma_bw
                 t = yield ("arrive", (c, "full", slot), tma_free[c])
@@ -333,7 +344,7 @@ def simulate_order(order="A", nt=128, nslots=6, lag_own=2, lag_peer=3, L_tma=150
                     t = yield ("wait", (c, "g_full", k2 & 1), k2 >> 1)
             else:
                 kp = tile // 2
-                if sub == 0:
+                if sub == 0 and not w_ring:
                     t = yield ("wait", (c, "w_full", 0), kp)
             used = []
             for _ in range(nslots_of(op)):
@@ -347,13 +358,18 @@ def simulate_order(order="A", nt=128, nslots=6, lag_own=2, lag_peer=3, L_tma=150
             pipe_free[c] = start + dur
             pipe_busy[c] += dur
             fin = pipe_free[c]
+            if w_ring and kind == "p":
+                if sub == 0:
+                    wpend, used = used[:2], used[2:]
+                else:
+                    used = used + wpend
             for u in used:
                 t = yield ("arrive", (c, "empty", u), fin + 30)
             if kind == "c" and sub == kch - 1:
                 t = yield ("arrive", (c, "s_full", (tile // 2) & 1), fin + 30)
             if kind == "o" and sub == 1:
                 t = yield ("arrive", (c, "s_empty", (tile // 2) & 1), fin + 30)
-            if kind == "p" and sub == 1:
+            if kind == "p" and sub == 1 and not w_ring:
                 t = yield ("arrive", (1 - c, "w_empty", 0), fin + 30 + ack)
             end_time[c] = max(end_time[c], fin)
 
@@ -370,6 +386,12 @@ def simulate_order(order="A", nt=128, nslots=6, lag_own=2, lag_peer=3, L_tma=150
             t = yield ("wait", (c, "g_full", k & 1), k >> 1)
             t = yield ("delay", 150)
             t = yield ("arrive", (c, "s_empty", k & 1))
+            if w_ring:
+                t = yield ("wait", (1 - c, "w_grant", 0), k)
+                t = yield ("delay", X)
+                for sl in wslots[1 - c][k]:
+                    t = yield ("arrive", (1 - c, "full", sl))
+                continue
             t = yield ("wait", (c, "w_empty", 0), k - 1)
             t = yield ("delay", X)
             t = yield ("arrive", (1 - c, "w_full", 0))
