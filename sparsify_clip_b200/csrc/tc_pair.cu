@@ -33,7 +33,10 @@ constexpr int kThreads = 512;
 constexpr int kEpiThreads = 256;
 constexpr int kSlotBytes = 128 * 64 * 2;   // one [128 x 64] 16-bit chunk
 constexpr int kMaxSlots = 8;
-constexpr int kAStat = 6;                  // K-chunks of A resident in smem; the rest stream with the column tile
+#ifndef SCB_PAIR_ASTAT
+#define SCB_PAIR_ASTAT 6                   // tuning experiments may override it (-DSCB_PAIR_ASTAT=4: ring of 8 slots)
+#endif
+constexpr int kAStat = SCB_PAIR_ASTAT;     // K-chunks of A resident in smem; the rest stream with the column tile
                                            // (frees ring slots: the ring, not the tensor pipe, was the bottleneck)
 constexpr int kSendPaceClk = 200;          // idle cycles between two 16-byte remote stores of a sender thread
 constexpr int kPeerLag = 3;                // MMA2 of a peer tile is issued this many steps after the tile (odd:
