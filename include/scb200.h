@@ -48,6 +48,9 @@ extern "C" {
 #define SCB_E_SHAPE (-3)     /* shape not supported on this path */
 #define SCB_E_DRIVER (-4)    /* cuTensorMapEncodeTiled unavailable / failed */
 
+/* ABI revision of this header.  scb_version() returns the revision the loaded library was BUILT against; a binding
+ * must refuse a library whose revision differs (argument lists may have changed). */
+#define SCB_ABI_VERSION 200
 int scb_version(void);
 const char* scb_last_error(void);
 /* Launch plan of a B x B pass with nA rows against nB columns (host-only arithmetic, no CUDA call):

@@ -61,23 +61,39 @@ def header_symbols():
     return sorted(set(re.findall(r"\b(scb_[a-z0-9_]+)\s*\(", src)))
 
 
+def header_abi_version():
+    with open(HEADER) as f:
+        m = re.search(r"#define\s+SCB_ABI_VERSION\s+(\d+)", f.read())
+    if not m:
+        raise RuntimeError(f"{HEADER}: SCB_ABI_VERSION not found")
+    return int(m.group(1))
+
+
 def load(build_if_missing=True):
-    """Load (building first if needed and nvcc is present) and type the library."""
+    """Load (building first if the sources are newer and nvcc is present) and type the library.
+
+    The build is serialised across processes by a file lock (every rank of a torchrun job imports this module at the same
+    moment).  A failed compile is an error, never a silent fall-back to a stale binary; only a box WITHOUT nvcc may use
+    a prebuilt library, and in every case the library's ABI revision must match include/scb200.h."""
     global _lib
     if _lib is not None:
         return _lib
     if build_if_missing:
-        try:
-            from . import build as _build
-            if _build.needs_build():
-                _build.build()
-        except Exception as exc:  # no nvcc on this box: a prebuilt .so must already be there
-            if not os.path.exists(LIB_PATH):
-                raise RuntimeError(f"libscb200.so is missing and could not be built: {exc}") from exc
+        from . import build as _build
+        if _build.have_nvcc():
+            _build.build_locked()
+        elif not os.path.exists(LIB_PATH):
+            raise RuntimeError("libscb200.so is missing and there is no nvcc to build it (there is no CPU fallback)")
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m sparsify_clip_b200.build` "
                            "(there is no CPU fallback)")
     lib = ctypes.CDLL(LIB_PATH)
+    lib.scb_version.argtypes = []
+    lib.scb_version.restype = ctypes.c_int
+    have, want = lib.scb_version(), header_abi_version()
+    if have != want:
+        raise RuntimeError(f"{LIB_PATH} was built for ABI revision {have}, include/scb200.h declares {want}: rebuild it "
+                           "(`python -m sparsify_clip_b200.build --force`)")
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

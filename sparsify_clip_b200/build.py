@@ -14,11 +14,24 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Wno-deprecated-gpu-targets"]
 
 
+# SCB_DEV=1 in the environment: development build (verbose, short watchdog; tracer and experiment knobs of the pair kernel)
+if os.environ.get("SCB_DEV"):
+    FLAGS += ["-DSCB_TC_WATCHDOG_VERBOSE", "-DSCB_TC_WATCHDOG_NS=3000000000ull", "-DSCB_PAIR_TRACE", "-DSCB_PAIR_EXPERIMENTS"]
+
+
 def _nvcc():
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
             return cand
     raise RuntimeError("nvcc not found")
+
+
+def have_nvcc():
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
 
 
 def needs_build():
@@ -29,30 +42,51 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile and link; every intermediate file carries this process id, the final rename is atomic."""
     if not force and not needs_build():
         return LIB
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    tag = f".{os.getpid()}"
     flags = FLAGS + (["-Xptxas", "-v"] if verbose else [])
     procs, objs = [], []
     for src in SOURCES:            # one nvcc per translation unit, in parallel
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", tag + ".o"))
         objs.append(obj)
         procs.append((src, subprocess.Popen([_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj],
                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
-    for src, p in procs:
-        out, _ = p.communicate()
-        if verbose or p.returncode:
-            sys.stderr.write(f"--- nvcc {src}\n{out}\n")
-        failed |= p.returncode != 0
-    if failed:
-        raise RuntimeError("nvcc failed")
-    subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB + ".tmp", *objs,
-                           "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
-    os.replace(LIB + ".tmp", LIB)
+    try:
+        for src, p in procs:
+            out, _ = p.communicate()
+            if verbose or p.returncode:
+                sys.stderr.write(f"--- nvcc {src}\n{out}\n")
+            failed |= p.returncode != 0
+        if failed:
+            raise RuntimeError("nvcc failed (see the compiler output above)")
+        tmp = LIB + tag + ".tmp"
+        subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", tmp, *objs,
+                               "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+        os.replace(tmp, LIB)
+    finally:
+        for obj in objs:
+            if os.path.exists(obj):
+                os.remove(obj)
     return LIB
 
 
+def build_locked(force=False, verbose=False):
+    """build() under an exclusive inter-process lock: the ranks of a multi-process job all import the package at once;
+    one compiles, the others wait and then find the library up to date."""
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            return build(force=force, verbose=verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_locked(force="--force" in sys.argv, verbose="-v" in sys.argv))

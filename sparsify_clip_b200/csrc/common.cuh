@@ -27,6 +27,41 @@ void scb_set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
+// ----------------------------------------------------------------------------- per-device launch state
+// Nothing below is keyed by "the first device seen": the SM count and the opt-in to > 48 KB of dynamic shared memory
+// (cudaFuncSetAttribute is per device / context) are cached per CUDA device in lock-free slots, so a process that
+// drives several GPUs (the reference wraps its model in DataParallel) gets the right value on each.
+#include <atomic>
+constexpr int kScbMaxDevices = 64;
+static inline int scb_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+inline int scb_num_sms() {
+  static std::atomic<int> cache[kScbMaxDevices];
+  const int dev = scb_current_device();
+  int n = (dev >= 0 && dev < kScbMaxDevices) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < kScbMaxDevices) cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+// `done` is one bit mask per kernel family (a function-local static of the launcher); idempotent, so a race between two
+// host threads only repeats the call
+template <typename... K>
+inline cudaError_t scb_opt_in_smem(std::atomic<unsigned long long>& done, int bytes, K... kernels) {
+  const int dev = scb_current_device();
+  const unsigned long long bit = (dev >= 0 && dev < kScbMaxDevices) ? (1ull << dev) : 0ull;
+  if (bit && (done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  const cudaError_t rs[] = {cudaFuncSetAttribute(kernels, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)...};
+  for (cudaError_t r : rs) if (r != cudaSuccess) e = r;
+  if (e == cudaSuccess && bit) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
 static inline bool scb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int scb_dtype_size(int dtype) { return dtype == SCB_F32 ? 4 : 2; }
 static inline bool scb_dtype_ok(int dtype) { return dtype == SCB_F32 || dtype == SCB_BF16 || dtype == SCB_F16; }

@@ -50,19 +50,27 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug must trap with a message, never hang the GPU.
+// Bounded wait.  A protocol bug must end the kernel, never hang the GPU (on a shared pool a hung device takes the
+// whole box down), so every wait carries a watchdog; it is set far above any legitimate stall (30 s of wall clock:
+// time slicing, profiler replay and TMEM-allocation waits are milliseconds) and traps without printing.  Development
+// builds (-DSCB_TC_WATCHDOG_VERBOSE, usually with a short -DSCB_TC_WATCHDOG_NS) also print which barrier is stuck.
 #ifndef SCB_TC_WATCHDOG_NS
-#define SCB_TC_WATCHDOG_NS 4000000000ull
+#define SCB_TC_WATCHDOG_NS 30000000000ull
 #endif
+static __device__ __noinline__ void watchdog_fire(int tag, uint32_t parity) {
+#ifdef SCB_TC_WATCHDOG_VERBOSE
+  printf("scb200 watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+         tag, parity);
+#else
+  (void)tag; (void)parity;
+#endif
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > SCB_TC_WATCHDOG_NS) {
-      printf("scb200 watchdog: block %d thread %d stuck on barrier tag %d parity %u\n", (int)blockIdx.x,
-             (int)threadIdx.x, tag, parity);
-      __trap();
-    }
+    if (globaltimer_ns() - t0 > SCB_TC_WATCHDOG_NS) watchdog_fire(tag, parity);
   }
 }
 

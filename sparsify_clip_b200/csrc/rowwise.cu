@@ -15,7 +15,7 @@ void scb_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* scb_last_error(void) { return g_err; }
-extern "C" int scb_version(void) { return 100; }
+extern "C" int scb_version(void) { return SCB_ABI_VERSION; }
 
 namespace {
 

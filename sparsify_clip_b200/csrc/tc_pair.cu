@@ -66,8 +66,10 @@ struct PairParams {
 #define SCB_PAIR_SHORT_W(P) 0
 #endif
 
-// Debug timeline: cluster 0 records (tag, tile, clock64) per role; kTraceCap events per (CTA rank, role).
+// Debug timeline (builds with -DSCB_PAIR_TRACE only; the shipped library compiles it out and keeps no mutable state):
+// cluster 0 records (tag, tile, clock64) per role; kTraceCap events per (CTA rank, role).
 constexpr int kTraceCap = 4096;
+#ifdef SCB_PAIR_TRACE
 struct Tracer {
   unsigned long long* base;
   uint32_t n;
@@ -83,6 +85,12 @@ struct Tracer {
     }
   }
 };
+#else
+struct Tracer {
+  __device__ __forceinline__ void init(unsigned long long*, int, uint32_t, int) {}
+  __device__ __forceinline__ void rec(uint32_t, uint32_t) {}
+};
+#endif
 
 enum {
   BAR_FULL = 0,                      // [kMaxSlots]
@@ -152,11 +160,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity,
   if (mbar_try_wait_cluster(bar, parity)) return;
   const uint64_t t0 = ptx::globaltimer_ns();
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (ptx::globaltimer_ns() - t0 > SCB_TC_WATCHDOG_NS) {
-      printf("scb200 watchdog (pair): block %d thread %d stuck on barrier tag %d parity %u\n", (int)blockIdx.x,
-             (int)threadIdx.x, tag, parity);
-      __trap();
-    }
+    if (ptx::globaltimer_ns() - t0 > SCB_TC_WATCHDOG_NS) ptx::watchdog_fire(tag, parity);
   }
 }
 // arrive::one on the barrier at the same CTA-relative offset in every CTA of `mask`, once all tcgen05 operations
@@ -243,7 +247,9 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0) {
     setmaxnreg_dec<80>();
     Tracer tr; tr.init(P.trace, pair_id, crank, 0);
+#ifdef SCB_PAIR_TRACE
     if (lane == 0) { tr.rec(0, (uint32_t)(ptx::globaltimer_ns() & 0xffffffffu)); tr.rec(0, (uint32_t)(ptx::globaltimer_ns() >> 32)); }
+#endif
     Ring ring{0u, 0xFFFFFFFFu};
     uint32_t a_empty_par = 1, item_cnt = 0;
     SCB_PAIR_FOR_SEGMENTS() {
@@ -652,8 +658,12 @@ int scb_make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int D, int6
 
 namespace {
 
-unsigned long long* g_pair_trace = nullptr;
-int g_pair_dbg = 0;
+#ifdef SCB_PAIR_TRACE
+std::atomic<unsigned long long*> g_pair_trace{nullptr};
+#endif
+#ifdef SCB_PAIR_EXPERIMENTS
+std::atomic<int> g_pair_dbg{0};
+#endif
 
 }  // namespace
 
@@ -685,8 +695,12 @@ int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
                 PairParams P, cudaStream_t s) {
   if (nA == 0) return 0;
   P.nA = nA; P.nB = nB; P.D = D;
-  P.trace = g_pair_trace;
-  P.dbg = g_pair_dbg;
+#ifdef SCB_PAIR_TRACE
+  P.trace = g_pair_trace.load();
+#endif
+#ifdef SCB_PAIR_EXPERIMENTS
+  P.dbg = g_pair_dbg.load();
+#endif
   P.kch = (D + 63) / 64;
   P.n_rb = (int)((nA + 127) / 128);
   P.n_jb = (int)((nB + 127) / 128);
@@ -708,18 +722,11 @@ int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
   rc = scb_make_tmap_2d(&tmB, Bm, nB, D, ldB, dtype);
   if (rc) return rc;
 
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_pair<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_pair<MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  const int num_sms = scb_num_sms();
+  static std::atomic<unsigned long long> attr_done{0};
+  {
+    const cudaError_t e = scb_opt_in_smem(attr_done, 232448, k_tc_pair<MODE, 0>, k_tc_pair<MODE, 8>);
     if (e != cudaSuccess) { scb_set_error("cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
   }
   int n_pairs = 1, pmax = 1;
   scb_pair_span_plan(P.n_rb, P.n_jb, num_sms, &n_pairs, &P.span, &pmax);
@@ -750,9 +757,22 @@ int scb_tc_pair_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll
   return launch_pair<M_LUNIF_GRAD>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
 }
 
-// debug: timeline buffer for the next pair launches (2 CTAs x 4 roles x 4096 events x 2 words of 8 bytes), or null
+// debug: timeline buffer for the next pair launches (2 CTAs x 4 roles x 4096 events x 2 words of 8 bytes), or null.
+// Only builds with -DSCB_PAIR_TRACE record anything; the shipped library rejects the call.
 extern "C" int scb_debug_pair_trace(void* buf) {
-  g_pair_trace = static_cast<unsigned long long*>(buf);
+#ifdef SCB_PAIR_TRACE
+  g_pair_trace.store(static_cast<unsigned long long*>(buf));
+  return 0;
+#else
+  SCB_CHECK_ARG(buf == nullptr, SCB_E_ARG, "scb_debug_pair_trace: this build has no tracer (-DSCB_PAIR_TRACE)");
+  return 0;
+#endif
+}
+int scb_tc_pair_set_dbg(int v) {
+#ifdef SCB_PAIR_EXPERIMENTS
+  g_pair_dbg.store(v);
+#else
+  (void)v;
+#endif
   return 0;
 }
-int scb_tc_pair_set_dbg(int v) { g_pair_dbg = v; return 0; }

@@ -584,7 +584,7 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld,
   return 0;
 }
 
-int g_tc_flags = 3;   // bit0: weight tile in TMEM (TS-mode MMA2) -- measured faster than the smem variant
+std::atomic<int> g_tc_flags{3};   // bit0: weight tile in TMEM (TS-mode MMA2) -- measured faster than the smem variant
                       // bit1: CTA-pair kernel (tc_pair.cu) for the gradient passes when 256 < D <= 512
 
 template <int MODE>
@@ -619,18 +619,11 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
   rc = make_tmap(&tmB, Bm, nB, D, ldB, dtype);
   if (rc) return rc;
 
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_pass<MODE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_pass<MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  const int num_sms = scb_num_sms();
+  static std::atomic<unsigned long long> attr_done{0};
+  {
+    const cudaError_t e = scb_opt_in_smem(attr_done, 232448, k_tc_pass<MODE, 0>, k_tc_pass<MODE, 8>);
     if (e != cudaSuccess) { scb_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
   }
   const int n_items = P.n_rb * (GRAD ? P.nsplit : 1) * P.jparts;
   const int grid = n_items < num_sms ? n_items : num_sms;
@@ -644,7 +637,7 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
 }  // namespace
 
 int scb_tc_pair_set_dbg(int);
-int scb_tc_set_flags(int flags) { int o = g_tc_flags; g_tc_flags = flags & 3; scb_tc_pair_set_dbg(flags >> 2); return o; }
+int scb_tc_set_flags(int flags) { const int o = g_tc_flags.exchange(flags & 3); scb_tc_pair_set_dbg(flags >> 2); return o; }
 int scb_make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype) {
   return make_tmap(m, base, rows, D, ld, dtype);
 }

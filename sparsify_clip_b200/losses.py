@@ -78,8 +78,9 @@ def _gout32(g):
 
 # ----------------------------------------------------------------------------- anchor (CLIP InfoNCE)
 class _AnchorFn(torch.autograd.Function):
-    """sparsify_clip.py:110-132.  forward: two LSE sweeps (rows of S, rows of S^T) + diagonal;
-    backward: one recompute sweep per operand (flash-style), d/dtau from the same sweep."""
+    """sparsify_clip.py:110-132.  forward: ONE sweep over S that yields the row and the column LSE (sharded: the row
+    LSE of the local rows of S and of S^T) + the diagonal; backward: one recompute sweep per operand (flash-style),
+    d/dtau from the dI sweep."""
 
     @staticmethod
     def forward(ctx, I, T, tau_t, tau_f, group):
@@ -182,6 +183,34 @@ def lunif_loss(x, t=2, *, group=None, mma_dtype=None):
 
 
 # ----------------------------------------------------------------------------- fused composition
+def _flatten(obj):
+    """Nested tuples / dicts with tensor leaves -> (list of tensors, spec) for ctx.save_for_backward."""
+    flat = []
+
+    def walk(o):
+        if isinstance(o, torch.Tensor):
+            flat.append(o)
+            return ("t", len(flat) - 1)
+        if isinstance(o, dict):
+            return ("d", {k: walk(v) for k, v in o.items()})
+        if isinstance(o, (tuple, list)):
+            return ("l", [walk(v) for v in o])
+        return ("c", o)
+
+    return flat, walk(obj)
+
+
+def _unflatten(tensors, spec):
+    kind, val = spec
+    if kind == "t":
+        return tensors[val]
+    if kind == "d":
+        return {k: _unflatten(tensors, v) for k, v in val.items()}
+    if kind == "l":
+        return tuple(_unflatten(tensors, v) for v in val)
+    return val
+
+
 class _FusedTermsFn(torch.autograd.Function):
     """w_a * contrastive_loss(I, T, tau) + w_l * lalign_loss(I, T) + w_i * lunif_loss(I) + w_t * lunif_loss(T)
     + w_c * lunif_loss(normalize((I + T) / 2))  (every composition of sparsify_clip.py:778-938) as ONE autograd node.
@@ -330,15 +359,17 @@ class _FusedTermsFn(torch.autograd.Function):
         ctx.in_dtypes = (I.dtype, T.dtype)
         ctx.out_dtypes = (I.dtype if I.dtype in okdt else torch.float32, T.dtype if T.dtype in okdt else torch.float32)
         ctx.need = (need_I, need_T)
-        ctx.terms = (Ip, Tp, an_I, an_T, un_I, un_T, 2.0 * w_l / B, cen)
-        ctx.dtau = dtau
+        # every tensor the backward reads goes through save_for_backward (autograd's version counters then catch an
+        # in-place update of the embeddings between forward and backward); the dict structure is rebuilt from a spec
+        flat, ctx.spec = _flatten((Ip, Tp, an_I, an_T, un_I, un_T, 2.0 * w_l / B, cen, dtau))
+        ctx.save_for_backward(*flat)
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         be = get_backend()
         g = _gout32(gout)
-        Ip, Tp, an_I, an_T, un_I, un_T, lc, cen = ctx.terms
+        Ip, Tp, an_I, an_T, un_I, un_T, lc, cen, dtau0 = _unflatten(ctx.saved_tensors, ctx.spec)
         dI = dT = dtau = None
         if ctx.need[0]:
             dI = be.grad_combine(Ip, Tp, ctx.out_dtypes[0], anchor=an_I, unif=un_I, l_coef=lc, dev_scale=g,
@@ -346,8 +377,8 @@ class _FusedTermsFn(torch.autograd.Function):
         if ctx.need[1]:
             dT = be.grad_combine(Tp, Ip, ctx.out_dtypes[1], anchor=an_T, unif=un_T, l_coef=lc, dev_scale=g,
                                  extra=cen, e_coef=1.0).to(ctx.in_dtypes[1])
-        if ctx.dtau is not None:
-            dtau = ctx.dtau * g.to(device=ctx.dtau.device, dtype=ctx.dtau.dtype)
+        if dtau0 is not None:
+            dtau = dtau0 * g.to(device=dtau0.device, dtype=dtau0.dtype)
         return dI, dT, dtau, None, None, None, None, None, None, None, None
 
 
@@ -391,6 +422,8 @@ class _LalignFn(torch.autograd.Function):
 def lalign_loss(x, y, alpha=2, *, group=None):
     if alpha != 2:
         # the reference only ever calls alpha=2 (all YAMLs); other exponents stay in PyTorch
+        if _resolve_group(group) is not None:
+            raise NotImplementedError("lalign_loss(alpha != 2) has no sharded form; only alpha = 2 is on the kernel path")
         return (x - y).norm(dim=1).pow(alpha).mean()
     return _LalignFn.apply(x, y, _resolve_group(group))
 
@@ -500,8 +533,8 @@ def sparsify_loss(x):
 
 def random_alignment_loss(x, y):
     """sparsify_clip.py:178-184: L_align against a random permutation of y."""
-    idx = torch.randperm(y.size(0), device=y.device)
-    return lalign_loss(x, y[idx])
+    idx = torch.randperm(y.size(0))          # CPU generator, like the reference (:181): seeds reproduce its stream
+    return lalign_loss(x, y[idx.to(y.device)])
 
 
 def contrastive_loss_roberta(image_embeds, text_embeds, roberta_similarity, temperature=0.07):

@@ -1,0 +1,162 @@
+"""GPU parity, part 2 (pytest -m gpu): the pre-loss normalise against the oracle, and the BASELINE
+configurations AT THEIR STATED SIZE against the slab-wise fp64 oracle (tests/_chunked_oracle.py, pinned against
+oracle/closed_form.py on CPU): loss, d/dtau and 64 sampled gradient rows.
+
+Tolerances: loss 1e-5 relative to the magnitude of its terms; bf16 tensor-core gradients 1e-3 of the
+gradient norm (Frobenius over the sampled rows).  The WORST single row is asserted separately and its bound is stated
+where it differs from 1e-3 (see _ROW_BOUND): a row whose gradient is dominated by one or two 2^-9-rounded weights
+carries that rounding undiluted."""
+import numpy as np
+import pytest
+import torch
+
+import sparsify_clip_b200 as scb
+from oracle import closed_form as cf
+from tests import _chunked_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+# Worst single-row relative error ||got_i - ref_i|| / ||ref_i|| allowed on the bf16 tensor-core path.  The gate of
+# BASELINE.md §5 (1e-3) is norm-wise; per row the 8-bit weight rounding (2^-9 relative per weight) averages over the
+# ~B weights of the row only when no single weight dominates.
+_ROW_BOUND = 3e-3
+
+
+def _synth(B, D, seed=42):
+    """SURVEY.md §8(d) synthetic inputs: I = normalize(randn), T = normalize(I + 0.5 randn), bf16-rounded."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    I = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device="cuda"), dim=-1)
+    T = torch.nn.functional.normalize(I + 0.5 * torch.randn(B, D, generator=g, device="cuda"), dim=-1)
+    return I.to(torch.bfloat16), T.to(torch.bfloat16)
+
+
+def _sample_rows(B, n=64, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    rows = torch.randperm(B, generator=g)[:n - 4]
+    return torch.cat([rows, torch.tensor([0, 127, 128, B - 1])]).unique().cuda()
+
+
+def _check_config(B, D, tau, w, learnable_tau, slab):
+    Iq, Tq = _synth(B, D)
+    rows = _sample_rows(B)
+    ref, dI, dT, dtau, terms = co.weighted(Iq.double(), Tq.double(), tau, w["anchor"], w["align"], w["unif_img"],
+                                           w["unif_txt"], w["unif_cen"], rows, slab=slab)
+    I, T = Iq.clone().requires_grad_(True), Tq.clone().requires_grad_(True)
+    tp = torch.nn.Parameter(torch.tensor(tau)) if learnable_tau else tau
+    loss = scb.weighted_loss(I, T, tp, w)
+    gscale = 8.0                                            # GradScaler-like grad_output (exact in bf16)
+    (loss * gscale).backward()
+    mag = sum(abs(w[k] * terms[t]) for k, t in (("anchor", "anchor"), ("align", "lalign"), ("unif_img", "lunif_img"),
+                                                ("unif_txt", "lunif_txt"), ("unif_cen", "lunif_centroids")) if t in terms)
+    assert abs(loss.item() - ref) <= 1e-5 * mag, (loss.item(), ref, terms)
+    out = {}
+    for name, got, want in (("dI", I.grad, dI), ("dT", T.grad, dT)):
+        got = got[rows].double() / gscale
+        fro = ((got - want).norm() / want.norm()).item()
+        row = ((got - want).norm(dim=1) / want.norm(dim=1)).max().item()
+        out[name] = (fro, row)
+        # the leaves are bf16 here (BASELINE c2-c4 dtype): the returned gradient is itself rounded to 8 bits, which alone
+        # is ~2^-9/sqrt(3) = 1.1e-3 per element; the 1e-3 gate is stated on the fp32 gradient (checked below)
+        assert fro <= 4e-3, (name, fro)
+    if learnable_tau:
+        assert abs(tp.grad.item() / gscale - dtau) <= 1e-3 * abs(dtau), (tp.grad.item() / gscale, dtau)
+    # same run with fp32 leaves holding the same bf16 values: gradients come back unrounded -> the 1e-3 gate proper
+    prev = scb.set_fp32_mode("bf16")
+    try:
+        I32, T32 = Iq.float().requires_grad_(True), Tq.float().requires_grad_(True)
+        tp = torch.nn.Parameter(torch.tensor(tau)) if learnable_tau else tau
+        loss32 = scb.weighted_loss(I32, T32, tp, w)
+        loss32.backward()
+    finally:
+        scb.set_fp32_mode(prev)
+    assert abs(loss32.item() - ref) <= 1e-5 * mag
+    for name, got, want in (("dI", I32.grad, dI), ("dT", T32.grad, dT)):
+        got = got[rows].double()
+        fro = ((got - want).norm() / want.norm()).item()
+        row = ((got - want).norm(dim=1) / want.norm(dim=1)).max().item()
+        print(f"[fullsize B={B} D={D}] {name}: sampled-rows Frobenius rel {fro:.2e}, worst row rel {row:.2e}")
+        assert fro <= 1e-3, (name, fro)
+        assert row <= _ROW_BOUND, (name, row)
+    if learnable_tau:
+        assert abs(tp.grad.item() - dtau) <= 1e-3 * abs(dtau)
+
+
+def test_c3_exp3_at_full_size_vs_chunked_fp64_oracle():
+    """BASELINE c3: exp 3 (anchor + lalign + (lunif(I) + lunif(T))/2), B = 32768, D = 512, learnable tau."""
+    _check_config(32768, 512, 0.1, dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0), True, 2048)
+
+
+def test_c4_shard_exp10_vs_chunked_fp64_oracle():
+    """BASELINE c4's composition (exp 10: anchor + alpha lalign + beta lunif(centroids), learnable tau, D = 768) at
+    B = 8192, mid-schedule weights (step = 0.6 t_total: beta = 0.2, alpha = 1.2; sparsify_clip.py:879-902)."""
+    alpha, beta = scb.get_alpha(600, 1000, 50, 50), scb.get_beta(600, 1000, 20, 50)
+    assert alpha == pytest.approx(1.2) and beta == pytest.approx(0.2)
+    _check_config(8192, 768, 0.1, dict(anchor=1.0, align=alpha, unif_img=0.0, unif_txt=0.0, unif_cen=beta), True, 2048)
+
+
+def test_c2_exp4_vs_chunked_fp64_oracle():
+    """BASELINE c2: exp 4 (anchor + lalign + lunif(centroids)), B = 4096, D = 512."""
+    _check_config(4096, 512, 0.1, dict(anchor=1.0, align=1.0, unif_img=0.0, unif_txt=0.0, unif_cen=1.0), False, 4096)
+
+
+def test_d1024_exp3_vs_chunked_fp64_oracle():
+    """The reference's real embedding width (open_clip RN50: D = 1024, experiments_configs/*.yaml:13), B = 4096."""
+    _check_config(4096, 1024, 0.07, dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0), True, 4096)
+
+
+@pytest.mark.parametrize("B,D,dtype", [(300, 512, torch.float32), (257, 768, torch.bfloat16), (129, 44, torch.float32),
+                                       (64, 1024, torch.float16), (1000, 100, torch.bfloat16), (5, 8, torch.float32)])
+def test_l2_normalize_forward_and_backward_vs_oracle(B, D, dtype):
+    """sparsify_clip.py:772-773: e / e.norm(dim=-1, keepdim=True) (no eps), forward and backward, non-unit rows,
+    D % 8 != 0 (scalar path), a non-trivial upstream gradient (grad_output != 1)."""
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + D)
+    x = (torch.randn(B, D, generator=g, device="cuda") * (0.1 + 5.0 * torch.rand(B, 1, generator=g, device="cuda"))).to(dtype)
+    up = torch.randn(B, D, generator=g, device="cuda") * 37.0          # d loss / d x_hat
+    xg = x.clone().requires_grad_(True)
+    y = scb.l2_normalize(xg)
+    y.backward(up.to(y.dtype))
+    xe = x.double().cpu().numpy()
+    want = cf.l2_normalize(xe)
+    dwant = cf.l2_normalize_backward(xe, up.to(y.dtype).double().cpu().numpy())
+    # forward: one rounding to the output dtype
+    ftol = {torch.float32: 2e-7, torch.bfloat16: 2 ** -8, torch.float16: 2 ** -11}[y.dtype]
+    assert np.abs(y.double().cpu().numpy() - want).max() <= ftol * np.abs(want).max() + 1e-30
+    gtol = 1e-5 if dtype == torch.float32 else ({torch.bfloat16: 6e-3, torch.float16: 1e-3}[dtype])   # gradient returned in the leaf dtype
+    got = xg.grad.double().cpu().numpy()
+    assert xg.grad.dtype == dtype
+    assert np.linalg.norm(got - dwant) <= gtol * np.linalg.norm(dwant)
+    rowerr = np.linalg.norm(got - dwant, axis=1) / np.maximum(np.linalg.norm(dwant, axis=1), 1e-30)
+    assert rowerr.max() <= 4 * gtol
+    # the result is unit-norm and the gradient is tangent to the sphere at x_hat
+    assert abs(np.linalg.norm(y.double().cpu().numpy(), axis=1) - 1.0).max() <= 4 * ftol
+    assert np.abs((got * want).sum(1)).max() <= 4 * gtol * np.linalg.norm(dwant, axis=1).max()
+
+
+def test_l2_normalize_then_loss_chain_gradient():
+    """normalise -> exp-4 composition -> backward through both (what the c5 caller runs): gradient w.r.t. the RAW
+    encoder outputs against the oracle chain cf.weighted_loss -> cf.l2_normalize_backward."""
+    B, D, tau = 384, 512, 0.1
+    g = torch.Generator(device="cuda").manual_seed(9)
+    e_i = torch.randn(B, D, generator=g, device="cuda") * 3.0
+    e_t = e_i + 1.5 * torch.randn(B, D, generator=g, device="cuda")
+    xi, xt = e_i.clone().requires_grad_(True), e_t.clone().requires_grad_(True)
+    w = dict(anchor=1.0, align=1.0, unif_img=0.0, unif_txt=0.0, unif_cen=1.0)
+    loss = scb.weighted_loss(scb.l2_normalize(xi), scb.l2_normalize(xt), tau, w)
+    loss.backward()
+    ei, et = e_i.double().cpu().numpy(), e_t.double().cpu().numpy()
+    ref, dI, dT, _, terms = cf.weighted_loss(cf.l2_normalize(ei), cf.l2_normalize(et), tau, 1.0, 1.0, 0.0, 0.0, 1.0)
+    assert abs(loss.item() - ref) <= 1e-5 * sum(abs(v) for v in terms.values())
+    for got, e, d in ((xi.grad, ei, dI), (xt.grad, et, dT)):
+        want = cf.l2_normalize_backward(e, d)
+        assert np.linalg.norm(got.double().cpu().numpy() - want) <= 1e-5 * np.linalg.norm(want)
+
+
+def test_random_alignment_loss_draws_from_the_cpu_generator_like_the_reference():
+    """sparsify_clip.py:181 draws torch.randperm on the CPU generator; the same seed must give the same permutation."""
+    I, T = _synth(256, 64)
+    torch.manual_seed(123)
+    a = scb.random_alignment_loss(I.float(), T.float()).item()
+    torch.manual_seed(123)
+    idx = torch.randperm(256)
+    b = cf.lalign_loss(I.float().cpu().numpy(), T.float().cpu().numpy()[idx.numpy()], need_grad=False)
+    assert a == pytest.approx(b, rel=1e-5)

@@ -123,3 +123,26 @@ def test_closed_form_vs_reference_autograd(B, D, tau):
     for step in (0, 150, 200, 450, 699, 700, 5000):
         assert cf.get_beta(step, 1000, 20, 50) == ref.get_beta(step, 1000, 20, 50)
         assert cf.get_alpha(step, 1000, 50, 50) == ref.get_alpha(step, 1000, 50, 50)
+
+
+@pytest.mark.parametrize("B,D,slab,w", [(200, 24, 64, (1.0, 1.0, 0.5, 0.5, 0.0)), (131, 16, 50, (1.0, 1.3, 0.0, 0.0, 0.7)),
+                                        (96, 8, 4096, (1.0, 0.7, 0.25, 0.25, 0.5))])
+def test_chunked_oracle_matches_the_closed_forms(B, D, slab, w):
+    """tests/_chunked_oracle.py (the slab-wise fp64 restatement used for full-size GPU parity) against
+    oracle/closed_form.py, which is pinned against the reference above: every term, sampled gradient rows, d/dtau;
+    slab sizes that do and do not divide B, duplicate rows included."""
+    from tests import _chunked_oracle as co
+    g = torch.Generator().manual_seed(B + D)
+    I = torch.nn.functional.normalize(torch.randn(B, D, generator=g, dtype=torch.float64), dim=-1)
+    T = torch.nn.functional.normalize(I + 0.5 * torch.randn(B, D, generator=g, dtype=torch.float64), dim=-1)
+    I[5] = I[17]                                   # an exact duplicate pair (d^2 clamps at 0)
+    rows = torch.tensor([0, 5, 17, B // 2, B - 1])
+    tau = 0.1
+    ref, dI, dT, dtau, terms = cf.weighted_loss(I.numpy(), T.numpy(), tau, *w)
+    got, gI, gT, gtau, gterms = co.weighted(I, T, tau, *w, rows, slab=slab)
+    assert got == pytest.approx(ref, rel=1e-12, abs=1e-12)
+    for k, v in terms.items():
+        assert gterms[k] == pytest.approx(v, rel=1e-12)
+    assert np.abs(gI.numpy() - dI[rows.numpy()]).max() <= 1e-13
+    assert np.abs(gT.numpy() - dT[rows.numpy()]).max() <= 1e-13
+    assert gtau == pytest.approx(dtau, rel=1e-11)
