@@ -120,7 +120,7 @@ def test_l2_normalize_forward_and_backward_vs_oracle(B, D, dtype):
     dwant = cf.l2_normalize_backward(xe, up.to(y.dtype).double().cpu().numpy())
     # forward: one rounding to the output dtype
     ftol = {torch.float32: 2e-7, torch.bfloat16: 2 ** -8, torch.float16: 2 ** -11}[y.dtype]
-    assert np.abs(y.double().cpu().numpy() - want).max() <= ftol * np.abs(want).max() + 1e-30
+    assert np.abs(y.detach().double().cpu().numpy() - want).max() <= ftol * np.abs(want).max() + 1e-30
     gtol = 1e-5 if dtype == torch.float32 else ({torch.bfloat16: 6e-3, torch.float16: 1e-3}[dtype])   # gradient returned in the leaf dtype
     got = xg.grad.double().cpu().numpy()
     assert xg.grad.dtype == dtype
@@ -128,7 +128,7 @@ def test_l2_normalize_forward_and_backward_vs_oracle(B, D, dtype):
     rowerr = np.linalg.norm(got - dwant, axis=1) / np.maximum(np.linalg.norm(dwant, axis=1), 1e-30)
     assert rowerr.max() <= 4 * gtol
     # the result is unit-norm and the gradient is tangent to the sphere at x_hat
-    assert abs(np.linalg.norm(y.double().cpu().numpy(), axis=1) - 1.0).max() <= 4 * ftol
+    assert abs(np.linalg.norm(y.detach().double().cpu().numpy(), axis=1) - 1.0).max() <= 4 * ftol
     assert np.abs((got * want).sum(1)).max() <= 4 * gtol * np.linalg.norm(dwant, axis=1).max()
 
 
