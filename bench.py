@@ -398,6 +398,7 @@ def run_ours(args):
     # ---- timed region: K steps, each bracketed by CUDA events, L2 flushed (untimed) in between
     first_row = len(sampler.rows)      # only samples taken from here on (the timed region) are reported
     gc0 = [g["collections"] for g in gc.get_stats()]
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     evs = []
     launches0 = be.launches
     barrier()
@@ -411,6 +412,7 @@ def run_ours(args):
     barrier()
     launches = be.launches - launches0
     gc_in_region = [g["collections"] - a for g, a in zip(gc.get_stats(), gc0)]
+    mallocs_in_region = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
     # A short timed region yields too few nvidia-smi samples (100 ms period; denser polling was measured to stall the
     # GPU: outlier steps of 2x): keep the same load running, untimed, for ~0.6 s more.  Rank 0 owns the sampler and
     # decides; the step count is broadcast so that every rank runs the same collectives.
@@ -536,6 +538,7 @@ def run_ours(args):
             "loss": loss_val,
             "step_ms_rank0": [round(x, 3) for x in step_ms],
             "python_gc_collections_in_timed_region": gc_in_region,      # per generation, rank 0
+            "cuda_mallocs_in_timed_region": mallocs_in_region,          # caching-allocator misses (each one syncs the device)
             "peak_device_memory_bytes_rank0": int(peak_mem),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * D * 2, "d2h_bytes_per_step": 4,
                     "ms_per_step": et.item(),

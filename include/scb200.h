@@ -56,12 +56,18 @@ const char* scb_last_error(void);
 /* Launch plan of a B x B pass with nA rows against nB columns (host-only arithmetic, no CUDA call):
  * *jparts = how many contiguous parts the column sweep is split into so that the work items fill
  * n_sm SMs evenly; *nsub = per-row statistic sub-partials each part writes (1 SIMT, 2 TC, 4 TC on a
- * CTA pair).  grad != 0 for the passes that also produce a [nA, D] output. */
+ * CTA pair or a cluster of 4).  grad != 0 for the passes that also produce a [nA, D] output. */
 int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, int n_sm, int* jparts, int* nsub);
 /* debug/tuning knobs for the TC path: bit0 = keep the weight tile in TMEM (TS-mode MMA) instead of
  * shared memory; bit1 = run the gradient passes on CTA pairs (cluster of 2, weight tile shared through
- * distributed shared memory) when 256 < D <= 512.  Returns the previous value. */
+ * distributed shared memory) when 256 < D <= 512; bit2 = run them on clusters of 4 with cta_group::2
+ * MMAs (two row blocks x two output halves) when additionally nA > 128.  Returns the previous value. */
 int scb_set_tc_flags(int flags);
+/* Which kernel a TC gradient pass over nA rows of width D runs on the current device:
+ * 0 = single CTA (k_tc_pass), 1 = CTA pair (k_tc_pair), 2 = cluster of 4 (k_tc_quad).  In *units (may be
+ * null): how many of those run concurrently (SMs, pairs, clusters).  The first call on a device asks the
+ * driver how many clusters of 4 fit (cudaOccupancyMaxActiveClusters); scb_pass_plan uses the same answer. */
+int scb_grad_kernel_kind(int64_t nA, int D, int n_sm, int* units);
 
 /* ------------------------------------------------------------------ row-wise kernels */
 

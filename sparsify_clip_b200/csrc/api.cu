@@ -18,8 +18,10 @@ int scb_tc_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64
                  int, float*, float*, float*, cudaStream_t);
 int scb_tc_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
 int scb_tc_set_flags(int);
-bool scb_tc_use_pair(int D, int grad);
+int scb_tc_grad_kernel(int64_t nA, int D, int grad);
+int scb_quad_clusters();
 void scb_pair_span_plan(int64_t n_rb, int64_t n_jb, int n_sm, int* n_pairs, int64_t* span, int* pmax);
+void scb_quad_span_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int* n_used, int64_t* span, int* pmax);
 
 #define SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path)                                           \
   SCB_CHECK_ARG(scb_dtype_ok(dtype), SCB_E_DTYPE, "%s: unsupported dtype %d", __func__, (int)(dtype));             \
@@ -51,7 +53,13 @@ extern "C" int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, 
   if (path == SCB_PATH_TC) {
     const int kch = (D + 63) / 64;
     const int64_t n_rb = (nA + 127) / 128, n_jb = (nB + 127) / 128;
-    if (scb_tc_use_pair(D, grad) && n_sm >= 2) {       // equal contiguous spans of (row block, tile) per CTA pair
+    const int kern = n_sm >= 2 ? scb_tc_grad_kernel(nA, D, grad) : 0;
+    if (kern == 2) {            // equal contiguous spans of (256-row block, tile) per cluster of 4 (tc_quad.cu); the
+      int nc = 0;               // number of co-resident clusters is a property of the current device, asked once
+      int64_t span = 0;
+      scb_quad_span_plan((nA + 255) / 256, n_jb, scb_quad_clusters(), &nc, &span, jparts);
+      *nsub = 4;
+    } else if (kern == 1) {     // equal contiguous spans of (row block, tile) per CTA pair
       int np = 0;
       int64_t span = 0;
       scb_pair_span_plan(n_rb, n_jb, n_sm, &np, &span, jparts);
@@ -71,6 +79,11 @@ extern "C" int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, 
   return 0;
 }
 extern "C" int scb_set_tc_flags(int flags) { return scb_tc_set_flags(flags); }
+extern "C" int scb_grad_kernel_kind(int64_t nA, int D, int n_sm, int* units) {
+  const int kern = n_sm >= 2 ? scb_tc_grad_kernel(nA, D, 1) : 0;
+  if (units) *units = kern == 2 ? scb_quad_clusters() : (kern == 1 ? n_sm / 2 : n_sm);
+  return kern;
+}
 
 extern "C" int scb_lse_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                             float scale, int jparts, float* part_m, float* part_l, int path, void* stream) {

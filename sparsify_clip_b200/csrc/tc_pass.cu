@@ -570,12 +570,12 @@ PFN_encodeTiled get_encode() {
   return fn;
 }
 
-int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype) {
+int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype, int box_rows = 128) {
   PFN_encodeTiled enc = get_encode();
   SCB_CHECK_ARG(enc != nullptr, SCB_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2u};
-  cuuint32_t box[2] = {64u, 128u};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = enc(m, dtype == SCB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -584,8 +584,9 @@ int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld,
   return 0;
 }
 
-std::atomic<int> g_tc_flags{3};   // bit0: weight tile in TMEM (TS-mode MMA2) -- measured faster than the smem variant
+std::atomic<int> g_tc_flags{7};   // bit0: weight tile in TMEM (TS-mode MMA2) -- measured faster than the smem variant
                       // bit1: CTA-pair kernel (tc_pair.cu) for the gradient passes when 256 < D <= 512
+                      // bit2: cluster-of-4 kernel (tc_quad.cu, cta_group::2 MMAs) for the same passes when nA > 128
 
 template <int MODE>
 int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
@@ -637,18 +638,31 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
 }  // namespace
 
 int scb_tc_pair_set_dbg(int);
-int scb_tc_set_flags(int flags) { const int o = g_tc_flags.exchange(flags & 3); scb_tc_pair_set_dbg(flags >> 2); return o; }
+int scb_quad_clusters();
+int scb_tc_set_flags(int flags) { const int o = g_tc_flags.exchange(flags & 7); scb_tc_pair_set_dbg(flags >> 3); return o; }
 int scb_make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype) {
   return make_tmap(m, base, rows, D, ld, dtype);
 }
-// the gradient passes run on a CTA pair (one S tile per two output halves) when the output needs two column groups
-bool scb_tc_use_pair(int D, int grad) {
+int scb_make_tmap_2d_box(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype, int box_rows) {
+  return make_tmap(m, base, rows, D, ld, dtype, box_rows);
+}
+// Which kernel runs a gradient pass on the tensor-core path: 0 = single CTA (k_tc_pass; D <= 256 needs no split, D > 512
+// sweeps once per 256-column output group), 1 = CTA pair (k_tc_pair), 2 = cluster of 4 with cta_group::2 MMAs (k_tc_quad).
+// The planner (scb_pass_plan) and the launchers both ask here, so they cannot disagree.
+int scb_tc_grad_kernel(int64_t nA, int D, int grad) {
   const int kch = (D + 63) / 64;
-  return grad && (g_tc_flags & 2) && kch > 4 && kch <= 8;
+  const int f = g_tc_flags.load();
+  if (!grad || kch <= 4 || kch > 8) return 0;
+  if ((f & 4) && nA > 128 && scb_quad_clusters() > 0) return 2;
+  return (f & 2) ? 1 : 0;
 }
 int scb_tc_pair_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*,
                             const float*, int64_t, int, float*, float*, cudaStream_t);
 int scb_tc_pair_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
+                      int64_t, int, float*, float*, float*, cudaStream_t);
+int scb_tc_quad_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*,
+                            const float*, int64_t, int, float*, float*, cudaStream_t);
+int scb_tc_quad_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
                       int64_t, int, float*, float*, float*, cudaStream_t);
 
 int scb_tc_lse(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype, float scale,
@@ -667,9 +681,12 @@ int scb_tc_lse2(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
 int scb_tc_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                        float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts, float* out,
                        float* ws, cudaStream_t s) {
-  if (scb_tc_use_pair(D, 1) && (dtype == SCB_BF16 || dtype == SCB_F16) && D % 8 == 0 && ldA % 8 == 0 && ldB % 8 == 0 &&
-      scb_aligned16(A) && scb_aligned16(Bm))
-    return scb_tc_pair_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s);
+  const int kern = scb_tc_grad_kernel(nA, D, 1);
+  if (kern && (dtype == SCB_BF16 || dtype == SCB_F16) && D % 8 == 0 && ldA % 8 == 0 && ldB % 8 == 0 && scb_aligned16(A) &&
+      scb_aligned16(Bm))
+    return kern == 2
+               ? scb_tc_quad_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s)
+               : scb_tc_pair_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s);
   TcParams P{};
   P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.rowvec = row_lse; P.colvec = col_lse; P.diag_off = diag_off;
   P.out = out; P.s0 = ws;
@@ -678,9 +695,12 @@ int scb_tc_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, in
 int scb_tc_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll, int dtype,
                  float t, const float* sqn_r, const float* sqn_all, int64_t row_offset, int jparts, float* U, float* rq,
                  float* rs, cudaStream_t s) {
-  if (U && scb_tc_use_pair(D, 1) && (dtype == SCB_BF16 || dtype == SCB_F16) && D % 8 == 0 && ldR % 8 == 0 &&
-      ldAll % 8 == 0 && scb_aligned16(Xr) && scb_aligned16(Xall))
-    return scb_tc_pair_lunif(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, t, sqn_r, sqn_all, row_offset, jparts, U, rq, rs, s);
+  const int kern = U ? scb_tc_grad_kernel(nR, D, 1) : 0;
+  if (kern && (dtype == SCB_BF16 || dtype == SCB_F16) && D % 8 == 0 && ldR % 8 == 0 && ldAll % 8 == 0 && scb_aligned16(Xr) &&
+      scb_aligned16(Xall))
+    return kern == 2
+               ? scb_tc_quad_lunif(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, t, sqn_r, sqn_all, row_offset, jparts, U, rq, rs, s)
+               : scb_tc_pair_lunif(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, t, sqn_r, sqn_all, row_offset, jparts, U, rq, rs, s);
   TcParams P{};
   P.jparts = jparts; P.p0 = t * SCB_LOG2E; P.rowvec = sqn_r; P.colvec = sqn_all; P.diag_off = row_offset;
   P.out = U; P.s0 = rq; P.s1 = rs;

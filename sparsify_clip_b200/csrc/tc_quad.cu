@@ -1,0 +1,817 @@
+// tc_quad.cu -- gradient passes on a CLUSTER OF FOUR CTAs (two cta_group::2 pairs, sm_100a) for 256 < D <= 512.
+//
+// k_tc_pair (tc_pair.cu) is bound by shared-memory bandwidth, not by the tensor pipe: its MMA1 is a single-CTA
+// M128.N128.K16 SS instruction that reads 8 KB of operands per 64 cycles -- all of an SM's 128 B/clk -- and every
+// column tile is pulled from L2 1.5 times per CTA (measured: tensor pipe 46 % active).  Here every MMA is a
+// cta_group::2 instruction: the two CTAs of a pair hold two DIFFERENT row blocks (M = 256) and each stages only HALF
+// of the B operand, which halves both the operand reads and the TMA fills per FLOP:
+//
+//   cluster = 2 pairs; pair h owns output columns [256 h, 256 h + 256); CTA c of a pair owns rows [128 c, 128 c + 128)
+//   of the 256-row block.  CTA rank in the cluster = 2 h + c (pairs are ranks {0,1} and {2,3}; rank 2h leads).
+//   tile t (128 columns) is owned by pair (t & 1):
+//     MMA1  S[256 x 128] = A[256 x D] . Bm_t[128 x D]^T     cta_group::2, M256 N128 K16; each CTA stages 64 rows of Bm_t
+//     epi   W = f(S) -> own TMEM (in place)                 each CTA its 128 rows, as in the pair kernel
+//     send  W -> the CTA with the same rows in the OTHER pair (rank ^ 2) through st.async (DSMEM), as in the pair kernel
+//   every tile, both pairs:
+//     MMA2  OUT[256 x 256] += W[256 x 128] . Bm_t[128 x 256(half h)]   cta_group::2, M256 N256 K16; each CTA stages the
+//           128 output columns [256 h + 128 c, +128) of the tile (own W from TMEM, the other pair's W from smem)
+//
+// Per CTA and tile pair: 4096 MMA cycles (as before), shared-memory traffic 480 KB (pair kernel: 768 KB), L2 -> SM
+// 160 KB (pair kernel: 288 KB).  Roles, register split, TMEM and smem maps are those of the pair kernel; what changes
+// is who signals whom -- the MMA issuer of a pair lives in its leader CTA, so every "ready" barrier it waits on is
+// completed by BOTH CTAs (TMA bytes of the mate land on the leader's barrier through the .cta_group::2 form of
+// cp.async.bulk.tensor; epilogue / sender warps of the mate arrive remotely), and every "free" signal is a
+// tcgen05.commit multicast to both CTAs.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+enum { M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2 };
+
+constexpr int kThreads = 512;
+constexpr int kEpiThreads = 256;
+constexpr int kSlotBytes = 128 * 64 * 2;   // one [128 x 64] 16-bit chunk (or two [64 x 64] half-tile chunks)
+constexpr int kHalfBytes = kSlotBytes / 2;
+constexpr int kMaxSlots = 8;
+#ifndef SCB_QUAD_ASTAT
+#define SCB_QUAD_ASTAT 6
+#endif
+constexpr int kAStat = SCB_QUAD_ASTAT;     // K-chunks of the row block resident in smem; the rest stream with the tiles
+constexpr int kSendPaceClk = 200;
+constexpr int kPeerLag = 3;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColOut = 0, kColS0 = 256;
+
+struct QuadParams {
+  int64_t nA, nB;
+  int D, kch, n_rp, n_jb, jparts, nslots, fmt;
+  int64_t span;                // tiles of the linearised (256-row block, column tile) space per cluster
+  float p0;
+  const float* rowvec;
+  const float* colvec;
+  int64_t diag_off;
+  float* out;  // [jparts][nA][D]
+  float* s0;   // anchor: ws ; lunif: rq     [jparts*4][nA]
+  float* s1;   // lunif: rs
+};
+
+enum {
+  BAR_FULL = 0,                      // [kMaxSlots]  leader: TMA bytes of BOTH CTAs of the pair
+  BAR_EMPTY = kMaxSlots,             // [kMaxSlots]  each CTA: tcgen05.commit multicast
+  BAR_A_FULL = 2 * kMaxSlots,        // leader
+  BAR_A_EMPTY,                       // each
+  BAR_S_FULL,                        // [2] each (multicast commit)
+  BAR_S_EMPTY = BAR_S_FULL + 2,      // [2] leader: MMA2 commit + 4 sender warps of each CTA = 9
+  BAR_G_FULL = BAR_S_EMPTY + 2,      // [2] each: the 8 local epilogue warps -> the local sender warps
+  BAR_G_MMA = BAR_G_FULL + 2,        // [2] leader: the 16 epilogue warps of the pair -> the MMA issuer
+  BAR_OUT_FULL = BAR_G_MMA + 2,      // each (multicast commit)
+  BAR_OUT_EMPTY,                     // leader: 16 epilogue warps
+  BAR_W_FULL,                        // each: 32 KB of st.async from rank ^ 2, armed locally by warp 1
+  BAR_W_MATE,                        // leader: the mate's W tile has landed (relayed by the mate's warp 1)
+  BAR_W_EMPTY,                       // each: the consuming pair's tcgen05.commit, multicast to both senders
+  BAR_COUNT
+};
+
+struct Ring {
+  uint32_t slot, bits;
+  __device__ __forceinline__ uint32_t take(uint32_t n) {
+    const uint32_t s = slot;
+    slot = (slot + 1 == n) ? 0u : slot + 1;
+    return s;
+  }
+  __device__ __forceinline__ uint32_t parity_then_flip(uint32_t s) {
+    const uint32_t p = (bits >> s) & 1u;
+    bits ^= (1u << s);
+    return p;
+  }
+};
+
+// ---- cluster / DSMEM / cta_group::2 helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t n_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d,
+                                            uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(remote_addr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar) : "memory");
+}
+// arrive on a barrier given by its shared::cluster address (own CTA or another CTA of the cluster)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+// waits on barriers that CTAs other than the waiter's complete: acquire at cluster scope
+__device__ __forceinline__ bool mbar_try_wait_cl(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait_cl(bar, parity)) return;
+  const uint64_t t0 = ptx::globaltimer_ns();
+  while (!mbar_try_wait_cl(bar, parity)) {
+    if (ptx::globaltimer_ns() - t0 > SCB_TC_WATCHDOG_NS) ptx::watchdog_fire(tag, parity);
+  }
+}
+// TMA tile load whose completion bytes are counted on a barrier of the pair's LEADER CTA (shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const CUtensorMap* m, int x, int y, uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive::one on the barrier at the same CTA-relative offset in every CTA of `mask`, once all cta_group::2 tcgen05
+// operations issued so far by this thread have completed
+__device__ __forceinline__ void umma_commit2(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int MODE, int KCH>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 1)
+k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmBh, const QuadParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in every CTA
+  const int kch = KCH ? KCH : P.kch;
+  const int n_astat = KCH ? (KCH < kAStat ? KCH : kAStat) : min(kch, kAStat);
+  const int n_bslots = (kch + 1) >> 1;                                      // ring slots of one half-tile of B (MMA1)
+  const int b1_slots = n_bslots + (kch - n_astat);                          // ring slots one S tile consumes
+  const uint32_t sm_a = smem_base;
+  const uint32_t sm_w = sm_a + (uint32_t)n_astat * kSlotBytes;              // Wrecv: 2 chunks
+  const uint32_t sm_ring = sm_w + 2u * kSlotBytes;
+  const uint32_t nslots = (uint32_t)P.nslots;
+  const uint32_t sm_cbuf = sm_ring + nslots * kSlotBytes;                   // 2 x 128 floats
+  const uint32_t sm_bar = sm_cbuf + 1024u;
+  const uint32_t sm_tmem_ptr = sm_bar + BAR_COUNT * 8u;
+  auto bar = [&](int i) -> uint32_t { return sm_bar + 8u * (uint32_t)i; };
+  uint8_t* gen_base = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  float* cbuf = reinterpret_cast<float*>(gen_base + (sm_cbuf - smem_base));
+  volatile uint32_t* tmem_ptr_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (sm_tmem_ptr - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r4 = cluster_ctarank();
+  const uint32_t h = r4 >> 1;                          // pair: which 256 output columns
+  const uint32_t c = r4 & 1u;                          // CTA in the pair: which 128 rows of the 256-row block
+  const bool leader = (c == 0);
+  const uint32_t lead_rank = r4 & ~1u;
+  const uint32_t xrank = r4 ^ 2u;                      // same rows, other pair: my W partner
+  const uint16_t pair_mask = (uint16_t)(3u << (2u * h));
+  const uint16_t xpair_mask = (uint16_t)(3u << (2u * (h ^ 1u)));
+  const int cluster_id = (int)cluster_id_x();
+  const int64_t total_tiles = (int64_t)P.n_rp * P.n_jb;
+  auto lbar = [&](int i) -> uint32_t { return mapa(bar(i), lead_rank); };   // the leader's copy of barrier i
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmBh);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kMaxSlots; ++i) { ptx::mbar_init(bar(BAR_FULL + i), 1); ptx::mbar_init(bar(BAR_EMPTY + i), 1); }
+    ptx::mbar_init(bar(BAR_A_FULL), 1);
+    ptx::mbar_init(bar(BAR_A_EMPTY), 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar(BAR_S_FULL + b), 1);
+      ptx::mbar_init(bar(BAR_S_EMPTY + b), 9);
+      ptx::mbar_init(bar(BAR_G_FULL + b), 8);
+      ptx::mbar_init(bar(BAR_G_MMA + b), 16);
+    }
+    ptx::mbar_init(bar(BAR_OUT_FULL), 1);
+    ptx::mbar_init(bar(BAR_OUT_EMPTY), 16);
+    ptx::mbar_init(bar(BAR_W_FULL), 1);
+    ptx::mbar_init(bar(BAR_W_MATE), 1);
+    ptx::mbar_init(bar(BAR_W_EMPTY), 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();            // every CTA's barriers are initialised before anything remote touches them
+  if (warp == 2) tmem_alloc2(sm_tmem_ptr, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_slot;
+
+  // Work distribution: the (256-row block, column tile) space is linearised row-block-major and cut into equal
+  // contiguous spans, one per cluster; a span decomposes into segments (row block, tile range); a segment's output
+  // partial index `jp` is its ordinal inside its row block.  `item_cnt` alternates which pair owns the even tiles.
+#define SCB_QUAD_FOR_SEGMENTS()                                                                               \
+  for (int64_t g = (int64_t)cluster_id * P.span, g_end = (g + P.span < total_tiles ? g + P.span : total_tiles); g < g_end; ++item_cnt)
+#define SCB_QUAD_ITEM_SETUP()                                                                              \
+  const int rp = (int)(g / P.n_jb);                                                                        \
+  const int jb_lo = (int)(g - (int64_t)rp * P.n_jb);                                                       \
+  const int nt = (int)(((int64_t)(P.n_jb - jb_lo) < g_end - g) ? (int64_t)(P.n_jb - jb_lo) : g_end - g);   \
+  const int jp = cluster_id - (int)(((int64_t)rp * P.n_jb) / P.span);                                      \
+  const int t_first = (int)((h ^ (item_cnt & 1u)) & 1u);  /* my pair's own tiles: t_first, t_first + 2, ... */ \
+  const int n_own = (nt > t_first) ? (nt - t_first + 1) / 2 : 0;                                           \
+  const int row0 = rp * 256 + 128 * (int)c;               /* first row of this CTA's row block */           \
+  g += nt;                                                                                                 \
+  (void)rp; (void)jp; (void)jb_lo; (void)n_own; (void)row0
+
+  // =========================================================================== TMA producer (every CTA)
+  if (warp == 0) {
+    setmaxnreg_dec<80>();
+    Ring ring{0u, 0xFFFFFFFFu};
+    uint32_t a_empty_par = 1, item_cnt = 0;
+    const uint32_t l_a_full = lbar(BAR_A_FULL);
+    SCB_QUAD_FOR_SEGMENTS() {
+      SCB_QUAD_ITEM_SETUP();
+      if (n_own > 0) {
+        ptx::mbar_wait(bar(BAR_A_EMPTY), a_empty_par, 100);
+        a_empty_par ^= 1;
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_expect_tx(bar(BAR_A_FULL), 2u * (uint32_t)n_astat * kSlotBytes);
+          for (int kc = 0; kc < n_astat; ++kc) tma_load_2d_2sm(sm_a + kc * kSlotBytes, &tmA, kc * 64, row0, l_a_full);
+        }
+        __syncwarp();
+      }
+      // one ring slot: `bytes` per CTA land in it through up to two TMA boxes; bytes == 0 burns the slot (padding)
+      auto slot_begin = [&](uint32_t bytes, int tag) -> uint32_t {
+        const uint32_t s = ring.take(nslots);
+        ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), tag);
+        if (leader && ptx::elect_one()) {
+          if (bytes) ptx::mbar_expect_tx(bar(BAR_FULL + s), 2u * bytes);
+          else ptx::mbar_arrive(bar(BAR_FULL + s));
+        }
+        __syncwarp();
+        return s;
+      };
+      auto load_full = [&](const CUtensorMap* tm, int x, int y, int tag) {          // one [128 x 64] chunk
+        const uint32_t s = slot_begin((uint32_t)kSlotBytes, tag);
+        if (ptx::elect_one()) tma_load_2d_2sm(sm_ring + s * kSlotBytes, tm, x, y, lbar(BAR_FULL + (int)s));
+        __syncwarp();
+      };
+      // my two 64-wide output chunks of tile tt (clamped into the matrix: columns beyond D are computed from some
+      // valid chunk and never stored)
+      auto load_v = [&](int tt, int tag) {
+        for (int u = 0; u < 2; ++u) {
+          int ch = 4 * (int)h + 2 * (int)c + u;
+          if (ch >= kch) ch = kch - 1;
+          load_full(&tmB, ch * 64, (jb_lo + tt) * 128, tag);
+        }
+      };
+      for (int t = t_first; t < nt + kPeerLag + 1; t += 2) {
+        if (t < nt) {
+          const int yb = (jb_lo + t) * 128 + 64 * (int)c;           // my half (64 rows) of the column tile
+          for (int m = 0; m < n_bslots; ++m) {
+            // streamed K-chunks of the row block ride just ahead of the half-tile chunk pair that needs them
+            for (int kc = 2 * m; kc < min(2 * m + 2, kch); ++kc)
+              if (kc >= n_astat) load_full(&tmA, kc * 64, row0, 119);
+            const int nck = min(2, kch - 2 * m);
+            const uint32_t s = slot_begin((uint32_t)nck * kHalfBytes, 120);
+            if (ptx::elect_one()) {
+              const uint32_t lb = lbar(BAR_FULL + (int)s);
+              for (int u = 0; u < nck; ++u)
+                tma_load_2d_2sm(sm_ring + s * kSlotBytes + u * kHalfBytes, &tmBh, (2 * m + u) * 64, yb, lb);
+            }
+            __syncwarp();
+          }
+          if (b1_slots & 1) (void)slot_begin(0u, 118);
+        }
+        if (t - 2 >= 0 && t - 2 < nt) load_v(t - 2, 121);
+        if (t - kPeerLag >= 0 && t - kPeerLag < nt) load_v(t - kPeerLag, 122);
+      }
+    }
+  }
+  // =========================================================================== MMA issuer (leader) / W relay (mate)
+  else if (warp == 1) {
+    setmaxnreg_dec<80>();
+    if (leader) {
+      Ring ring{0u, 0u};
+      uint32_t a_full_par = 0, out_empty_par = 1, item_cnt = 0;
+      uint32_t k1 = 0, k2 = 0, kp = 0;   // issued MMA1 (own tiles), MMA2 on own tiles, MMA2 on the other pair's tiles
+      const uint32_t idesc1 = ptx::idesc_f16(256, 128, P.fmt, P.fmt, 0, 0);
+      const uint32_t idesc2 = ptx::idesc_f16(256, 256, P.fmt, P.fmt, 0, 1);
+      const uint32_t a_lo0 = ptx::desc_lo(sm_a, 16);
+      const uint32_t w_lo0 = ptx::desc_lo(sm_w, 16);
+      const uint32_t ring_lo0 = ptx::desc_lo(sm_ring, 16);
+      const uint32_t ring_v_lo0 = ptx::desc_lo(sm_ring, kSlotBytes);   // MN-major V: 64-wide blocks one chunk apart
+      constexpr uint32_t kChunkLo = kSlotBytes >> 4;
+      constexpr uint32_t kHalfLo = kHalfBytes >> 4;
+      SCB_QUAD_FOR_SEGMENTS() {
+        SCB_QUAD_ITEM_SETUP();
+        if (n_own > 0) {
+          mbar_wait_cl(bar(BAR_A_FULL), a_full_par, 200);
+          a_full_par ^= 1;
+        }
+        int own_left = n_own;
+        auto mma1 = [&]() {
+          const uint32_t b = k1 & 1u;
+          mbar_wait_cl(bar(BAR_S_EMPTY + b), ((k1 >> 1) & 1u) ^ 1u, 210);
+          const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
+          auto kpair = [&](int m) {
+            // ring order (see the producer): streamed A chunks of this K-chunk pair first, then the half-tile slot
+            uint32_t alo[2], sa[2] = {0, 0};
+            bool streamed[2] = {false, false};
+            const int nck = min(2, kch - 2 * m);
+            for (int u = 0; u < nck; ++u) {
+              const int kc = 2 * m + u;
+              if (kc >= n_astat) {
+                streamed[u] = true;
+                sa[u] = ring.take(nslots);
+                mbar_wait_cl(bar(BAR_FULL + sa[u]), ring.parity_then_flip(sa[u]), 211);
+                alo[u] = ring_lo0 + sa[u] * kChunkLo;
+              } else {
+                alo[u] = a_lo0 + (uint32_t)kc * kChunkLo;
+              }
+            }
+            const uint32_t s = ring.take(nslots);
+            mbar_wait_cl(bar(BAR_FULL + s), ring.parity_then_flip(s), 212);
+            ptx::tc_fence_after();
+            const uint32_t blo = ring_lo0 + s * kChunkLo;
+            if (ptx::elect_one()) {
+              for (int u = 0; u < nck; ++u) {
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                  umma_ss2(d_tmem, ptx::desc_join(alo[u] + 2u * k), ptx::desc_join(blo + (uint32_t)u * kHalfLo + 2u * k), idesc1,
+                           (uint32_t)((m | u | (int)k) != 0));
+                if (streamed[u]) umma_commit2(bar(BAR_EMPTY + sa[u]), pair_mask);
+              }
+              umma_commit2(bar(BAR_EMPTY + s), pair_mask);
+            }
+            __syncwarp();
+          };
+          if constexpr (KCH > 0) {
+#pragma unroll
+            for (int m = 0; m < (KCH + 1) / 2; ++m) kpair(m);
+          } else {
+#pragma unroll 1
+            for (int m = 0; m < n_bslots; ++m) kpair(m);
+          }
+          if (b1_slots & 1) {     // padding slot (keeps the V pairs on even slots)
+            const uint32_t s = ring.take(nslots);
+            mbar_wait_cl(bar(BAR_FULL + s), ring.parity_then_flip(s), 213);
+            if (ptx::elect_one()) umma_commit2(bar(BAR_EMPTY + s), pair_mask);
+            __syncwarp();
+          }
+          --own_left;
+          if (ptx::elect_one()) {
+            umma_commit2(bar(BAR_S_FULL + b), pair_mask);
+            if (own_left == 0) umma_commit2(bar(BAR_A_EMPTY), pair_mask);
+          }
+          __syncwarp();
+          ++k1;
+        };
+        auto mma2 = [&](bool own, bool first, bool last) {
+          uint32_t b = 0;
+          if (own) {
+            b = k2 & 1u;
+            mbar_wait_cl(bar(BAR_G_MMA + b), (k2 >> 1) & 1u, 220);
+          } else {
+            if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL), 2u * kSlotBytes);
+            __syncwarp();
+            mbar_wait_cl(bar(BAR_W_FULL), kp & 1u, 225);
+            mbar_wait_cl(bar(BAR_W_MATE), kp & 1u, 226);
+            ptx::fence_proxy_async_smem();
+          }
+          if (first) {
+            mbar_wait_cl(bar(BAR_OUT_EMPTY), out_empty_par, 221);
+            out_empty_par ^= 1;
+          }
+          const uint32_t g_tmem = tmem_base + kColS0 + 128u * b;
+          const uint32_t sv = ring.take(nslots);
+          mbar_wait_cl(bar(BAR_FULL + sv), ring.parity_then_flip(sv), 222);
+          const uint32_t sv1 = ring.take(nslots);
+          mbar_wait_cl(bar(BAR_FULL + sv1), ring.parity_then_flip(sv1), 223);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + kColOut;
+          const uint32_t vlo = ring_v_lo0 + sv * kChunkLo;
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < 8; ++ks) {
+              const uint64_t bdesc = ptx::desc_join(vlo + 128u * ks);
+              const uint32_t accum = (uint32_t)!(first && ks == 0);
+              if (own)
+                umma_ts2(d_tmem, g_tmem + (ks >> 2) * 64u + (ks & 3u) * 8u, bdesc, idesc2, accum);
+              else
+                umma_ss2(d_tmem, ptx::desc_join(w_lo0 + (ks >> 2) * kChunkLo + (ks & 3u) * 2u), bdesc, idesc2, accum);
+            }
+            umma_commit2(bar(BAR_EMPTY + sv), pair_mask);
+            umma_commit2(bar(BAR_EMPTY + sv1), pair_mask);
+            if (own) umma_commit2(bar(BAR_S_EMPTY + b), (uint16_t)(1u << lead_rank));
+            else umma_commit2(bar(BAR_W_EMPTY), xpair_mask);
+            if (last) umma_commit2(bar(BAR_OUT_FULL), pair_mask);
+          }
+          __syncwarp();
+          if (own) ++k2; else ++kp;
+        };
+        int m2_left = nt;          // the first MMA2 of the item overwrites OUT, the last one publishes it
+        for (int t = t_first; t < nt + kPeerLag + 1; t += 2) {
+          if (t < nt) mma1();
+          if (t - 2 >= 0 && t - 2 < nt) { mma2(true, m2_left == nt, m2_left == 1); --m2_left; }
+          if (t - kPeerLag >= 0 && t - kPeerLag < nt) { mma2(false, m2_left == nt, m2_left == 1); --m2_left; }
+        }
+      }
+    } else {
+      // mate: tell the leader's MMA issuer when the other pair's W tile for MY rows has landed in my Wrecv
+      uint32_t kp = 0, item_cnt = 0;
+      const uint32_t l_w_mate = lbar(BAR_W_MATE);
+      SCB_QUAD_FOR_SEGMENTS() {
+        SCB_QUAD_ITEM_SETUP();
+        const int n_peer = nt - n_own;
+        for (int i = 0; i < n_peer; ++i, ++kp) {
+          if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL), 2u * kSlotBytes);
+          __syncwarp();
+          mbar_wait_cl(bar(BAR_W_FULL), kp & 1u, 230);
+          ptx::fence_proxy_async_smem();
+          if (ptx::elect_one()) mbar_arrive_cluster(l_w_mate);
+          __syncwarp();
+        }
+      }
+    }
+  }
+  // =========================================================================== idle warps (TMEM allocator, spare)
+  else if (warp < 4) {
+    setmaxnreg_dec<80>();
+  }
+  // =========================================================================== epilogue warps (every CTA, its 128 rows)
+  else if (warp < 12) {
+    setmaxnreg_inc<168>();
+    const int e = warp - 4;
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int hh = e >> 2;        // which 64-column half of the S tile
+    const int rrow = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const uint32_t l_g_mma[2] = {lbar(BAR_G_MMA), lbar(BAR_G_MMA + 1)};
+    const uint32_t l_out_empty = lbar(BAR_OUT_EMPTY);
+    uint32_t ke = 0, item_cnt = 0;
+    SCB_QUAD_FOR_SEGMENTS() {
+      SCB_QUAD_ITEM_SETUP();
+      const int64_t gi = (int64_t)row0 + rrow;
+      const bool row_ok = gi < P.nA;
+      float rowc = 0.f;
+      if (MODE == M_ANCHOR_GRAD) rowc = row_ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
+      if (MODE == M_LUNIF_GRAD) rowc = row_ok ? P.rowvec[gi] * P.p0 : 0.f;
+      float st0 = 0.f, st1 = 0.f;
+      const int64_t my_diag_col = gi + P.diag_off;
+
+      for (int t = t_first; t < nt; t += 2, ++ke) {
+        const uint32_t b = ke & 1u;
+        const int jb = jb_lo + t;
+        const int64_t col0 = (int64_t)jb * 128 + 64 * hh;
+        const bool tile_partial = ((int64_t)jb * 128 + 128) > P.nB;
+        {
+          const int idx = e * 32 + lane;
+          if (idx < 128) {
+            const int64_t gj = (int64_t)jb * 128 + idx;
+            float cv = INFINITY;
+            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * P.p0;
+            cbuf[b * 128 + idx] = cv;
+          }
+          ptx::named_bar_sync(1, kEpiThreads);
+        }
+        ptx::mbar_wait(bar(BAR_S_FULL + b), (ke >> 1) & 1u, 300);
+        ptx::tc_fence_after();
+        const int64_t drow0 = (int64_t)row0 + 32 * q + P.diag_off;
+        const bool diag_here = (drow0 < col0 + 64) && (drow0 + 32 > col0);
+
+        uint32_t packed[32];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b + 64u * hh + 32u * cc, v);
+          ptx::tmem_ld_wait();
+          const int64_t cbase = col0 + 32 * cc;
+          const float* cb = cbuf + b * 128 + 64 * hh + 32 * cc;
+          const int dcol = diag_here ? (int)(my_diag_col - cbase) : -1;
+          if (tile_partial && MODE == M_ANCHOR_GRAD) {
+            const int nvalid = (int)min((int64_t)32, max((int64_t)0, P.nB - cbase));
+#pragma unroll
+            for (int cx = 0; cx < 32; ++cx)
+              if (cx >= nvalid) v[cx] = __float_as_uint(-1e30f);
+          }
+          float w[32];
+          if (MODE == M_ANCHOR_GRAD) {
+#pragma unroll
+            for (int cx = 0; cx < 32; ++cx) {
+              const float gg = __uint_as_float(v[cx]);
+              const float y = gg * P.p0;
+              const float ww = scb_ex2(y - rowc) + scb_ex2(y - cb[cx]);   // dead columns: 0 + 0
+              st0 = fmaf(ww, gg, st0);
+              w[cx] = ww;
+            }
+          } else {  // lunif: exp2(2 p0 g - p0 n_i - p0 n_j); dead columns carry +inf in cb -> 0
+            const float two_p0 = 2.f * P.p0;
+#pragma unroll
+            for (int cx = 0; cx < 32; ++cx) w[cx] = scb_ex2(fmaf(__uint_as_float(v[cx]), two_p0, -(rowc + cb[cx])));
+          }
+          if (diag_here) {
+#pragma unroll
+            for (int cx = 0; cx < 32; ++cx)
+              if (cx == dcol) w[cx] = 0.f;
+          }
+#pragma unroll
+          for (int cx = 0; cx < 16; ++cx) {
+            const uint32_t pk = P.fmt ? ptx::pack_bf16(w[2 * cx], w[2 * cx + 1]) : ptx::pack_f16(w[2 * cx], w[2 * cx + 1]);
+            packed[16 * cc + cx] = pk;
+            if (MODE == M_LUNIF_GRAD) {
+              st1 += w[2 * cx] + w[2 * cx + 1];
+              if (P.fmt) {
+                st0 += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
+              } else {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                st0 += f.x + f.y;
+              }
+            }
+          }
+        }
+        // ---- own copy: weights overwrite the first 32 columns of this warp's half of the S buffer (TS-mode MMA2)
+        ptx::tmem_st32(tmem_base + lane_addr + kColS0 + 128u * b + 64u * hh, packed);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(bar(BAR_G_FULL + b));          // my CTA's sender warps
+          mbar_arrive_cluster(l_g_mma[b]);                // the pair's MMA issuer
+        }
+      }  // own tiles
+
+      // ---- drain my quarter of the output accumulator (my 128 rows x my pair's 256 columns)
+      if (nt > 0) {
+        ptx::mbar_wait(bar(BAR_OUT_FULL), item_cnt & 1u, 320);
+        ptx::tc_fence_after();
+        float* orow = P.out + ((int64_t)jp * P.nA + gi) * P.D;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t v[32];
+          const int ocol = hh * 128 + c0;
+          ptx::tmem_ld32(tmem_base + lane_addr + kColOut + (uint32_t)ocol, v);
+          ptx::tmem_ld_wait();
+          const int d0 = 256 * (int)h + ocol;
+          if (row_ok) {
+            if (d0 + 32 <= P.D) {
+#pragma unroll
+              for (int cx = 0; cx < 32; cx += 4)
+                *reinterpret_cast<float4*>(orow + d0 + cx) = make_float4(__uint_as_float(v[cx]), __uint_as_float(v[cx + 1]),
+                                                                          __uint_as_float(v[cx + 2]), __uint_as_float(v[cx + 3]));
+            } else {
+#pragma unroll
+              for (int cx = 0; cx < 32; ++cx)
+                if (d0 + cx < P.D) orow[d0 + cx] = __uint_as_float(v[cx]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_out_empty);
+      }
+      if (row_ok) {   // statistics over MY pair's tiles only: 4 sub-partials per part (pair x column half)
+        const int64_t o = ((int64_t)jp * 4 + 2 * (int)h + hh) * P.nA + gi;
+        if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
+        if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
+      }
+      // A row block is covered by 1 .. jparts segments; the consumers sum all `jparts` partial slots, so the segment
+      // that finishes the row block clears the slots nobody writes.
+      if (row_ok && jb_lo + nt == P.n_jb) {
+        for (int sl = jp + 1; sl < P.jparts; ++sl) {
+          const int dbase = 256 * (int)h + hh * 128;
+          float* orow = P.out + ((int64_t)sl * P.nA + gi) * P.D + dbase;
+          for (int cx = 0; cx < 128; cx += 4) {
+            if (dbase + cx + 4 <= P.D) *reinterpret_cast<float4*>(orow + cx) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else for (int c2 = 0; c2 < 4; ++c2) if (dbase + cx + c2 < P.D) orow[cx + c2] = 0.f;
+          }
+          const int64_t o = ((int64_t)sl * 4 + 2 * (int)h + hh) * P.nA + gi;
+          if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = 0.f;
+          if (MODE == M_LUNIF_GRAD) { P.s0[o] = 0.f; P.s1[o] = 0.f; }
+        }
+      }
+    }  // items
+  }
+  // =========================================================================== W senders (every CTA -> rank ^ 2)
+  else {
+    setmaxnreg_dec<96>();
+    const int q = warp & 3;
+    const int rrow = 32 * q + lane;
+    const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+    const uint32_t peer_w = mapa(sm_w, xrank);
+    const uint32_t peer_w_full = mapa(bar(BAR_W_FULL), xrank);
+    const uint32_t l_s_empty[2] = {lbar(BAR_S_EMPTY), lbar(BAR_S_EMPTY + 1)};
+    uint32_t kx = 0, item_cnt = 0;
+    SCB_QUAD_FOR_SEGMENTS() {
+      SCB_QUAD_ITEM_SETUP();
+      for (int t = t_first; t < nt; t += 2, ++kx) {
+        const uint32_t b = kx & 1u;
+        ptx::mbar_wait(bar(BAR_G_FULL + b), (kx >> 1) & 1u, 400);
+        ptx::tc_fence_after();
+        uint32_t w0[32], w1[32];     // the two 64-column halves of my 32 rows of W (packed 16-bit pairs)
+        ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b, w0);
+        ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b + 64u, w1);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(l_s_empty[b]);
+        // K-major SW128 image in the partner's Wrecv, once the other pair has consumed the previous tile
+        ptx::mbar_wait(bar(BAR_W_EMPTY), (kx & 1u) ^ 1u, 410);
+        const uint32_t row_addr = peer_w + (uint32_t)rrow * 128u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          st_async_v4(row_addr + (uint32_t)((u ^ (rrow & 7)) << 4), w0[4 * u], w0[4 * u + 1], w0[4 * u + 2], w0[4 * u + 3],
+                      peer_w_full);
+          { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          st_async_v4(row_addr + kSlotBytes + (uint32_t)((u ^ (rrow & 7)) << 4), w1[4 * u], w1[4 * u + 1], w1[4 * u + 2],
+                      w1[4 * u + 3], peer_w_full);
+          { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
+        }
+      }
+    }
+  }
+#undef SCB_QUAD_ITEM_SETUP
+#undef SCB_QUAD_FOR_SEGMENTS
+
+  // =========================================================================== teardown
+  // nobody leaves while another CTA may still write into this CTA's shared memory, signal its barriers or (through a
+  // cta_group::2 MMA) touch its TMEM
+  ptx::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    tmem_dealloc2(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int scb_make_tmap_2d_box(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype, int box_rows);   // tc_pass.cu
+
+// Span plan of the quad kernel: clusters used, tiles per cluster, and the largest number of segments any 256-row block
+// is cut into (= output partial slots the caller must provide, "jparts").
+void scb_quad_span_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int* n_used, int64_t* span, int* pmax) {
+  const int64_t total = n_rp * n_jb;
+  int64_t nc = n_clusters;
+  if (nc > total) nc = total;
+  if (nc < 1) nc = 1;
+  int64_t sp = (total + nc - 1) / nc;
+  if (sp < (n_jb + 14) / 15) sp = (n_jb + 14) / 15;      // at most 16 partial slots per row block
+  if (sp < 1) sp = 1;
+  nc = (total + sp - 1) / sp;
+  int mx = 1;
+  for (int64_t rp = 0; rp < n_rp; ++rp) {
+    const int64_t first = (rp * n_jb) / sp, last = ((rp + 1) * n_jb - 1) / sp;
+    if ((int)(last - first + 1) > mx) mx = (int)(last - first + 1);
+  }
+  *n_used = (int)(nc < 1 ? 1 : nc);
+  *span = sp;
+  *pmax = mx;
+}
+
+namespace {
+
+constexpr int kQuadSmem = 232448;
+
+template <int MODE>
+int quad_max_clusters() {
+  // how many clusters of 4 CTAs (1 CTA per SM: 227 KB of shared memory each) the current device holds at once
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(4 * 64);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kQuadSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k_tc_quad<MODE, 8>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+std::atomic<int> g_quad_clusters[kScbMaxDevices];     // 0 = not asked yet, -1 = unavailable
+
+}  // namespace
+
+// Clusters of 4 the current device runs concurrently (cached per device); 0 when the device cannot run the kernel.
+int scb_quad_clusters() {
+  const int dev = scb_current_device();
+  if (dev < 0 || dev >= kScbMaxDevices) return 0;
+  int n = g_quad_clusters[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    static std::atomic<unsigned long long> attr_done{0};
+    if (scb_opt_in_smem(attr_done, kQuadSmem, k_tc_quad<M_ANCHOR_GRAD, 0>, k_tc_quad<M_ANCHOR_GRAD, 8>,
+                        k_tc_quad<M_LUNIF_GRAD, 0>, k_tc_quad<M_LUNIF_GRAD, 8>) != cudaSuccess) {
+      cudaGetLastError();
+      n = -1;
+    } else {
+      n = quad_max_clusters<M_LUNIF_GRAD>();
+      if (n <= 0) n = -1;
+    }
+    g_quad_clusters[dev].store(n, std::memory_order_relaxed);
+  }
+  return n > 0 ? n : 0;
+}
+
+namespace {
+
+template <int MODE>
+int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                QuadParams P, cudaStream_t s) {
+  if (nA == 0) return 0;
+  P.nA = nA; P.nB = nB; P.D = D;
+  P.kch = (D + 63) / 64;
+  P.n_rp = (int)((nA + 255) / 256);
+  P.n_jb = (int)((nB + 127) / 128);
+  SCB_CHECK_ARG(P.kch > 4 && P.kch <= 8, SCB_E_SHAPE, "quad kernel needs 256 < D <= 512 (D=%d)", D);
+  P.fmt = (dtype == SCB_BF16) ? 1 : 0;
+  const int budget = kQuadSmem - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
+  const int n_astat = P.kch < kAStat ? P.kch : kAStat;
+  int nslots = (budget - (n_astat + 2) * kSlotBytes) / kSlotBytes;
+  nslots &= ~1;
+  if (nslots > kMaxSlots) nslots = kMaxSlots;
+  SCB_CHECK_ARG(nslots >= 4, SCB_E_SHAPE, "not enough shared memory for the chunk ring (D=%d)", D);
+  P.nslots = nslots;
+  const size_t smem = (size_t)(n_astat + 2 + nslots) * kSlotBytes + 3 * 1024;
+
+  CUtensorMap tmA, tmB, tmBh;
+  int rc = scb_make_tmap_2d_box(&tmA, A, nA, D, ldA, dtype, 128);
+  if (rc) return rc;
+  rc = scb_make_tmap_2d_box(&tmB, Bm, nB, D, ldB, dtype, 128);
+  if (rc) return rc;
+  rc = scb_make_tmap_2d_box(&tmBh, Bm, nB, D, ldB, dtype, 64);
+  if (rc) return rc;
+
+  const int n_cl = scb_quad_clusters();
+  SCB_CHECK_ARG(n_cl > 0, SCB_E_SHAPE, "this device cannot run clusters of 4 CTAs with 227 KB of shared memory");
+  int n_used = 1, pmax = 1;
+  scb_quad_span_plan(P.n_rp, P.n_jb, n_cl, &n_used, &P.span, &pmax);
+  SCB_CHECK_ARG(P.jparts == pmax, SCB_E_ARG, "quad kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
+                P.jparts, pmax);
+  if (P.kch == 8) k_tc_quad<MODE, 8><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
+  else k_tc_quad<MODE, 0><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
+  SCB_CHECK_LAUNCH("tc_quad");
+  return 0;
+}
+
+}  // namespace
+
+int scb_tc_quad_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                            float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts,
+                            float* out, float* ws, cudaStream_t s) {
+  QuadParams P{};
+  P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.rowvec = row_lse; P.colvec = col_lse; P.diag_off = diag_off;
+  P.out = out; P.s0 = ws;
+  return launch_quad<M_ANCHOR_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
+}
+int scb_tc_quad_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll, int dtype,
+                      float t, const float* sqn_r, const float* sqn_all, int64_t row_offset, int jparts, float* U,
+                      float* rq, float* rs, cudaStream_t s) {
+  QuadParams P{};
+  P.jparts = jparts; P.p0 = t * SCB_LOG2E; P.rowvec = sqn_r; P.colvec = sqn_all; P.diag_off = row_offset;
+  P.out = U; P.s0 = rq; P.s1 = rs;
+  return launch_quad<M_LUNIF_GRAD>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
+}

@@ -148,7 +148,10 @@ def test_l2_normalize_then_loss_chain_gradient():
     assert abs(loss.item() - ref) <= 1e-5 * sum(abs(v) for v in terms.values())
     for got, e, d in ((xi.grad, ei, dI), (xt.grad, et, dT)):
         want = cf.l2_normalize_backward(e, d)
-        assert np.linalg.norm(got.double().cpu().numpy() - want) <= 1e-5 * np.linalg.norm(want)
+        # the projection removes the (large) radial part of d: the fp32 error of the chain is relative to the size of what
+        # goes INTO the projection, d / |e|, not to the (much smaller) tangential remainder that comes out
+        scale = np.linalg.norm(d / np.linalg.norm(e, axis=1, keepdims=True))
+        assert np.linalg.norm(got.double().cpu().numpy() - want) <= 1e-5 * scale, (np.linalg.norm(want), scale)
 
 
 def test_random_alignment_loss_draws_from_the_cpu_generator_like_the_reference():
