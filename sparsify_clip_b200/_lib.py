@@ -8,7 +8,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscb200.so")
+LIB_PATH = os.path.join(HERE, "libscb200" + os.environ.get("SCB_LIB_SUFFIX", "") + ".so")   # suffix: tuning variants only
 HEADER = os.path.join(os.path.dirname(HERE), "include", "scb200.h")
 
 SCB_F32, SCB_BF16, SCB_F16 = 0, 1, 2

@@ -6,7 +6,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libscb200.so")
+# SCB_LIB_SUFFIX / SCB_EXTRA_FLAGS (tuning experiments): build a variant library next to the shipped one
+LIB = os.path.join(HERE, "libscb200" + os.environ.get("SCB_LIB_SUFFIX", "") + ".so")
 SOURCES = ["rowwise.cu", "simt_pass.cu", "tc_pass.cu", "tc_pair.cu", "tc_quad.cu", "api.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "scb200.h")]
 # no --use_fast_math: the SIMT path is the exact fp32 path (expf/exp2f/division must stay IEEE-accurate)
@@ -15,6 +16,9 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 
 
 # SCB_DEV=1 in the environment: development build (verbose, short watchdog; tracer and experiment knobs of the pair kernel)
+FLAGS += os.environ.get("SCB_EXTRA_FLAGS", "").split()
+if os.environ.get("SCB_TRACE"):          # timeline tracer only (tools/pair_trace.py, tools/quad_trace.py), release speed otherwise
+    FLAGS += ["-DSCB_PAIR_TRACE"]
 if os.environ.get("SCB_DEV"):
     FLAGS += ["-DSCB_TC_WATCHDOG_VERBOSE", "-DSCB_TC_WATCHDOG_NS=3000000000ull", "-DSCB_PAIR_TRACE", "-DSCB_PAIR_EXPERIMENTS"]
 

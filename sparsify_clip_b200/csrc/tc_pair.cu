@@ -757,6 +757,13 @@ int scb_tc_pair_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll
   return launch_pair<M_LUNIF_GRAD>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
 }
 
+unsigned long long* scb_pair_trace_buffer() {
+#ifdef SCB_PAIR_TRACE
+  return g_pair_trace.load();
+#else
+  return nullptr;
+#endif
+}
 // debug: timeline buffer for the next pair launches (2 CTAs x 4 roles x 4096 events x 2 words of 8 bytes), or null.
 // Only builds with -DSCB_PAIR_TRACE record anything; the shipped library rejects the call.
 extern "C" int scb_debug_pair_trace(void* buf) {

@@ -35,11 +35,23 @@ constexpr int kSlotBytes = 128 * 64 * 2;   // one [128 x 64] 16-bit chunk (or tw
 constexpr int kHalfBytes = kSlotBytes / 2;
 constexpr int kMaxSlots = 8;
 #ifndef SCB_QUAD_ASTAT
-#define SCB_QUAD_ASTAT 6
+#define SCB_QUAD_ASTAT 4
 #endif
 constexpr int kAStat = SCB_QUAD_ASTAT;     // K-chunks of the row block resident in smem; the rest stream with the tiles
-constexpr int kSendPaceClk = 200;
-constexpr int kPeerLag = 3;
+#ifndef SCB_QUAD_PACE
+#define SCB_QUAD_PACE 100
+#endif
+#ifndef SCB_QUAD_LAG
+#define SCB_QUAD_LAG 5
+#endif
+#ifndef SCB_QUAD_WBUF
+#define SCB_QUAD_WBUF 2
+#endif
+constexpr int kWBuf = SCB_QUAD_WBUF;          // landing buffers for the other pair's weight tile (1 or 2).  With ONE buffer the
+                                              // hand-over is a serial chain -- consume, release, 32 KB of remote stores (~4200
+                                              // cycles measured), consume -- and that chain, not the tensor pipe, set the period
+constexpr int kSendPaceClk = SCB_QUAD_PACE;   // idle cycles between two 16-byte remote stores of a sender thread
+constexpr int kPeerLag = SCB_QUAD_LAG;        // MMA2 of the other pair's tile is issued this many steps after the tile (odd)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColOut = 0, kColS0 = 256;
 
@@ -54,7 +66,33 @@ struct QuadParams {
   float* out;  // [jparts][nA][D]
   float* s0;   // anchor: ws ; lunif: rq     [jparts*4][nA]
   float* s1;   // lunif: rs
+  unsigned long long* trace;   // debug timeline (-DSCB_PAIR_TRACE builds, scb_debug_pair_trace), normally null
 };
+
+// Debug timeline (builds with -DSCB_PAIR_TRACE only): cluster 0 records (tag, tile, clock64) per (CTA rank, role).
+constexpr int kTraceCap = 4096;
+#ifdef SCB_PAIR_TRACE
+struct Tracer {
+  unsigned long long* base;
+  uint32_t n;
+  __device__ __forceinline__ void init(unsigned long long* trace, int cluster_id, uint32_t rank, int role) {
+    base = (trace && cluster_id == 0) ? trace + ((size_t)(rank * 4 + role) * kTraceCap) * 2 : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void rec(uint32_t tag, uint32_t tile) {
+    if (base && n < kTraceCap) {
+      base[2 * n] = ((unsigned long long)tag << 32) | tile;
+      base[2 * n + 1] = (unsigned long long)clock64();
+      ++n;
+    }
+  }
+};
+#else
+struct Tracer {
+  __device__ __forceinline__ void init(unsigned long long*, int, uint32_t, int) {}
+  __device__ __forceinline__ void rec(uint32_t, uint32_t) {}
+};
+#endif
 
 enum {
   BAR_FULL = 0,                      // [kMaxSlots]  leader: TMA bytes of BOTH CTAs of the pair
@@ -67,10 +105,10 @@ enum {
   BAR_G_MMA = BAR_G_FULL + 2,        // [2] leader: the 16 epilogue warps of the pair -> the MMA issuer
   BAR_OUT_FULL = BAR_G_MMA + 2,      // each (multicast commit)
   BAR_OUT_EMPTY,                     // leader: 16 epilogue warps
-  BAR_W_FULL,                        // each: 32 KB of st.async from rank ^ 2, armed locally by warp 1
-  BAR_W_MATE,                        // leader: the mate's W tile has landed (relayed by the mate's warp 1)
-  BAR_W_EMPTY,                       // each: the consuming pair's tcgen05.commit, multicast to both senders
-  BAR_COUNT
+  BAR_W_FULL,                        // [2] each: 32 KB of st.async from rank ^ 2, armed locally by warp 1
+  BAR_W_MATE = BAR_W_FULL + 2,       // [2] leader: the mate's W tile has landed (relayed by the mate's warp 1)
+  BAR_W_EMPTY = BAR_W_MATE + 2,      // [2] each: the consuming pair's tcgen05.commit, multicast to both senders
+  BAR_COUNT = BAR_W_EMPTY + 2
 };
 
 struct Ring {
@@ -189,8 +227,8 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int n_bslots = (kch + 1) >> 1;                                      // ring slots of one half-tile of B (MMA1)
   const int b1_slots = n_bslots + (kch - n_astat);                          // ring slots one S tile consumes
   const uint32_t sm_a = smem_base;
-  const uint32_t sm_w = sm_a + (uint32_t)n_astat * kSlotBytes;              // Wrecv: 2 chunks
-  const uint32_t sm_ring = sm_w + 2u * kSlotBytes;
+  const uint32_t sm_w = sm_a + (uint32_t)n_astat * kSlotBytes;              // Wrecv: kWBuf x 2 chunks
+  const uint32_t sm_ring = sm_w + 2u * kWBuf * kSlotBytes;
   const uint32_t nslots = (uint32_t)P.nslots;
   const uint32_t sm_cbuf = sm_ring + nslots * kSlotBytes;                   // 2 x 128 floats
   const uint32_t sm_bar = sm_cbuf + 1024u;
@@ -230,9 +268,11 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     ptx::mbar_init(bar(BAR_OUT_FULL), 1);
     ptx::mbar_init(bar(BAR_OUT_EMPTY), 16);
-    ptx::mbar_init(bar(BAR_W_FULL), 1);
-    ptx::mbar_init(bar(BAR_W_MATE), 1);
-    ptx::mbar_init(bar(BAR_W_EMPTY), 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(bar(BAR_W_FULL + b), 1);
+      ptx::mbar_init(bar(BAR_W_MATE + b), 1);
+      ptx::mbar_init(bar(BAR_W_EMPTY + b), 1);
+    }
     ptx::fence_barrier_init();
   }
   __syncthreads();
@@ -263,6 +303,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // =========================================================================== TMA producer (every CTA)
   if (warp == 0) {
     setmaxnreg_dec<80>();
+    Tracer tr; tr.init(P.trace, cluster_id, r4, 0);
     Ring ring{0u, 0xFFFFFFFFu};
     uint32_t a_empty_par = 1, item_cnt = 0;
     const uint32_t l_a_full = lbar(BAR_A_FULL);
@@ -281,6 +322,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       auto slot_begin = [&](uint32_t bytes, int tag) -> uint32_t {
         const uint32_t s = ring.take(nslots);
         ptx::mbar_wait(bar(BAR_EMPTY + s), ring.parity_then_flip(s), tag);
+        if (lane == 0) tr.rec((uint32_t)tag, s);
         if (leader && ptx::elect_one()) {
           if (bytes) ptx::mbar_expect_tx(bar(BAR_FULL + s), 2u * bytes);
           else ptx::mbar_arrive(bar(BAR_FULL + s));
@@ -329,6 +371,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   else if (warp == 1) {
     setmaxnreg_dec<80>();
     if (leader) {
+      Tracer tr; tr.init(P.trace, cluster_id, r4, 1);
       Ring ring{0u, 0u};
       uint32_t a_full_par = 0, out_empty_par = 1, item_cnt = 0;
       uint32_t k1 = 0, k2 = 0, kp = 0;   // issued MMA1 (own tiles), MMA2 on own tiles, MMA2 on the other pair's tiles
@@ -349,7 +392,9 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         int own_left = n_own;
         auto mma1 = [&]() {
           const uint32_t b = k1 & 1u;
+          if (lane == 0) tr.rec(10, k1);
           mbar_wait_cl(bar(BAR_S_EMPTY + b), ((k1 >> 1) & 1u) ^ 1u, 210);
+          if (lane == 0) tr.rec(11, k1);
           const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
           auto kpair = [&](int m) {
             // ring order (see the producer): streamed A chunks of this K-chunk pair first, then the half-tile slot
@@ -369,6 +414,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             const uint32_t s = ring.take(nslots);
             mbar_wait_cl(bar(BAR_FULL + s), ring.parity_then_flip(s), 212);
+            if (lane == 0) tr.rec(12, (uint32_t)m);
             ptx::tc_fence_after();
             const uint32_t blo = ring_lo0 + s * kChunkLo;
             if (ptx::elect_one()) {
@@ -406,16 +452,19 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         };
         auto mma2 = [&](bool own, bool first, bool last) {
           uint32_t b = 0;
+          if (lane == 0) tr.rec(own ? 20 : 30, own ? k2 : kp);
           if (own) {
             b = k2 & 1u;
             mbar_wait_cl(bar(BAR_G_MMA + b), (k2 >> 1) & 1u, 220);
           } else {
-            if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL), 2u * kSlotBytes);
+            const uint32_t wb = kp % kWBuf, wpar = (kp / kWBuf) & 1u;
+            if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL + wb), 2u * kSlotBytes);
             __syncwarp();
-            mbar_wait_cl(bar(BAR_W_FULL), kp & 1u, 225);
-            mbar_wait_cl(bar(BAR_W_MATE), kp & 1u, 226);
+            mbar_wait_cl(bar(BAR_W_FULL + wb), wpar, 225);
+            mbar_wait_cl(bar(BAR_W_MATE + wb), wpar, 226);
             ptx::fence_proxy_async_smem();
           }
+          if (lane == 0) tr.rec(own ? 21 : 31, own ? k2 : kp);
           if (first) {
             mbar_wait_cl(bar(BAR_OUT_EMPTY), out_empty_par, 221);
             out_empty_par ^= 1;
@@ -425,6 +474,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           mbar_wait_cl(bar(BAR_FULL + sv), ring.parity_then_flip(sv), 222);
           const uint32_t sv1 = ring.take(nslots);
           mbar_wait_cl(bar(BAR_FULL + sv1), ring.parity_then_flip(sv1), 223);
+          if (lane == 0) tr.rec(own ? 22 : 32, own ? k2 : kp);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + kColOut;
           const uint32_t vlo = ring_v_lo0 + sv * kChunkLo;
@@ -436,15 +486,16 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if (own)
                 umma_ts2(d_tmem, g_tmem + (ks >> 2) * 64u + (ks & 3u) * 8u, bdesc, idesc2, accum);
               else
-                umma_ss2(d_tmem, ptx::desc_join(w_lo0 + (ks >> 2) * kChunkLo + (ks & 3u) * 2u), bdesc, idesc2, accum);
+                umma_ss2(d_tmem, ptx::desc_join(w_lo0 + (2u * (kp % kWBuf) + (ks >> 2)) * kChunkLo + (ks & 3u) * 2u), bdesc, idesc2, accum);
             }
             umma_commit2(bar(BAR_EMPTY + sv), pair_mask);
             umma_commit2(bar(BAR_EMPTY + sv1), pair_mask);
             if (own) umma_commit2(bar(BAR_S_EMPTY + b), (uint16_t)(1u << lead_rank));
-            else umma_commit2(bar(BAR_W_EMPTY), xpair_mask);
+            else umma_commit2(bar(BAR_W_EMPTY + (kp % kWBuf)), xpair_mask);
             if (last) umma_commit2(bar(BAR_OUT_FULL), pair_mask);
           }
           __syncwarp();
+          if (lane == 0) tr.rec(own ? 23 : 33, own ? k2 : kp);
           if (own) ++k2; else ++kp;
         };
         int m2_left = nt;          // the first MMA2 of the item overwrites OUT, the last one publishes it
@@ -457,16 +508,17 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     } else {
       // mate: tell the leader's MMA issuer when the other pair's W tile for MY rows has landed in my Wrecv
       uint32_t kp = 0, item_cnt = 0;
-      const uint32_t l_w_mate = lbar(BAR_W_MATE);
+      const uint32_t l_w_mate[2] = {lbar(BAR_W_MATE), lbar(BAR_W_MATE + 1)};
       SCB_QUAD_FOR_SEGMENTS() {
         SCB_QUAD_ITEM_SETUP();
         const int n_peer = nt - n_own;
         for (int i = 0; i < n_peer; ++i, ++kp) {
-          if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL), 2u * kSlotBytes);
+          const uint32_t wb = kp % kWBuf, wpar = (kp / kWBuf) & 1u;
+          if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL + wb), 2u * kSlotBytes);
           __syncwarp();
-          mbar_wait_cl(bar(BAR_W_FULL), kp & 1u, 230);
+          mbar_wait_cl(bar(BAR_W_FULL + wb), wpar, 230);
           ptx::fence_proxy_async_smem();
-          if (ptx::elect_one()) mbar_arrive_cluster(l_w_mate);
+          if (ptx::elect_one()) mbar_arrive_cluster(l_w_mate[wb]);
           __syncwarp();
         }
       }
@@ -487,6 +539,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t l_g_mma[2] = {lbar(BAR_G_MMA), lbar(BAR_G_MMA + 1)};
     const uint32_t l_out_empty = lbar(BAR_OUT_EMPTY);
     uint32_t ke = 0, item_cnt = 0;
+    Tracer tr; tr.init(e == 0 ? P.trace : nullptr, cluster_id, r4, 2);
     SCB_QUAD_FOR_SEGMENTS() {
       SCB_QUAD_ITEM_SETUP();
       const int64_t gi = (int64_t)row0 + rrow;
@@ -512,7 +565,9 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           ptx::named_bar_sync(1, kEpiThreads);
         }
+        if (lane == 0) tr.rec(40, ke);
         ptx::mbar_wait(bar(BAR_S_FULL + b), (ke >> 1) & 1u, 300);
+        if (lane == 0) tr.rec(41, ke);
         ptx::tc_fence_after();
         const int64_t drow0 = (int64_t)row0 + 32 * q + P.diag_off;
         const bool diag_here = (drow0 < col0 + 64) && (drow0 + 32 > col0);
@@ -575,6 +630,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) {
           ptx::mbar_arrive(bar(BAR_G_FULL + b));          // my CTA's sender warps
           mbar_arrive_cluster(l_g_mma[b]);                // the pair's MMA issuer
+          tr.rec(42, ke);
         }
       }  // own tiles
 
@@ -634,15 +690,17 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int q = warp & 3;
     const int rrow = 32 * q + lane;
     const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-    const uint32_t peer_w = mapa(sm_w, xrank);
-    const uint32_t peer_w_full = mapa(bar(BAR_W_FULL), xrank);
+    const uint32_t peer_w0 = mapa(sm_w, xrank);
+    const uint32_t peer_w_full2[2] = {mapa(bar(BAR_W_FULL), xrank), mapa(bar(BAR_W_FULL + 1), xrank)};
     const uint32_t l_s_empty[2] = {lbar(BAR_S_EMPTY), lbar(BAR_S_EMPTY + 1)};
     uint32_t kx = 0, item_cnt = 0;
+    Tracer tr; tr.init(q == 0 ? P.trace : nullptr, cluster_id, r4, 3);
     SCB_QUAD_FOR_SEGMENTS() {
       SCB_QUAD_ITEM_SETUP();
       for (int t = t_first; t < nt; t += 2, ++kx) {
         const uint32_t b = kx & 1u;
         ptx::mbar_wait(bar(BAR_G_FULL + b), (kx >> 1) & 1u, 400);
+        if (lane == 0) tr.rec(50, kx);
         ptx::tc_fence_after();
         uint32_t w0[32], w1[32];     // the two 64-column halves of my 32 rows of W (packed 16-bit pairs)
         ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b, w0);
@@ -652,20 +710,24 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(l_s_empty[b]);
         // K-major SW128 image in the partner's Wrecv, once the other pair has consumed the previous tile
-        ptx::mbar_wait(bar(BAR_W_EMPTY), (kx & 1u) ^ 1u, 410);
-        const uint32_t row_addr = peer_w + (uint32_t)rrow * 128u;
+        const uint32_t wb = kx % kWBuf;
+        ptx::mbar_wait(bar(BAR_W_EMPTY + wb), ((kx / kWBuf) & 1u) ^ 1u, 410);
+        if (lane == 0) tr.rec(51, kx);
+        const uint32_t peer_w_full = peer_w_full2[wb];
+        const uint32_t row_addr = peer_w0 + wb * 2u * kSlotBytes + (uint32_t)rrow * 128u;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           st_async_v4(row_addr + (uint32_t)((u ^ (rrow & 7)) << 4), w0[4 * u], w0[4 * u + 1], w0[4 * u + 2], w0[4 * u + 3],
                       peer_w_full);
-          { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
+          if (kSendPaceClk) { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           st_async_v4(row_addr + kSlotBytes + (uint32_t)((u ^ (rrow & 7)) << 4), w1[4 * u], w1[4 * u + 1], w1[4 * u + 2],
                       w1[4 * u + 3], peer_w_full);
-          { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
+          if (kSendPaceClk) { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
         }
+        if (lane == 0) tr.rec(52, kx);
       }
     }
   }
@@ -686,6 +748,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 }  // namespace
 
+unsigned long long* scb_pair_trace_buffer();   // tc_pair.cu (null unless built with -DSCB_PAIR_TRACE and armed)
 int scb_make_tmap_2d_box(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype, int box_rows);   // tc_pass.cu
 
 // Span plan of the quad kernel: clusters used, tiles per cluster, and the largest number of segments any 256-row block
@@ -763,6 +826,7 @@ int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
                 QuadParams P, cudaStream_t s) {
   if (nA == 0) return 0;
   P.nA = nA; P.nB = nB; P.D = D;
+  P.trace = scb_pair_trace_buffer();
   P.kch = (D + 63) / 64;
   P.n_rp = (int)((nA + 255) / 256);
   P.n_jb = (int)((nB + 127) / 128);
@@ -770,12 +834,12 @@ int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
   P.fmt = (dtype == SCB_BF16) ? 1 : 0;
   const int budget = kQuadSmem - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
   const int n_astat = P.kch < kAStat ? P.kch : kAStat;
-  int nslots = (budget - (n_astat + 2) * kSlotBytes) / kSlotBytes;
+  int nslots = (budget - (n_astat + 2 * kWBuf) * kSlotBytes) / kSlotBytes;
   nslots &= ~1;
   if (nslots > kMaxSlots) nslots = kMaxSlots;
   SCB_CHECK_ARG(nslots >= 4, SCB_E_SHAPE, "not enough shared memory for the chunk ring (D=%d)", D);
   P.nslots = nslots;
-  const size_t smem = (size_t)(n_astat + 2 + nslots) * kSlotBytes + 3 * 1024;
+  const size_t smem = (size_t)(n_astat + 2 * kWBuf + nslots) * kSlotBytes + 3 * 1024;
 
   CUtensorMap tmA, tmB, tmBh;
   int rc = scb_make_tmap_2d_box(&tmA, A, nA, D, ldA, dtype, 128);
