@@ -63,9 +63,14 @@ def parse():
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed sharded-parity block at N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tc-flags", type=int, default=None, help="debug: scb_set_tc_flags value")
-    ap.add_argument("--graph", action="store_true", help="replay the step from a captured CUDA graph (measured: no gain "
-                                                         "at c3, the step is kernel-bound; useful at small B)")
+    ap.add_argument("--launch", default="auto", choices=["auto", "graph", "eager"],
+                    help="how a step is launched: 'graph' = the whole step (library kernels and, at N > 1, the NCCL collectives) "
+                         "captured once into a CUDA graph and replayed; 'eager' = ~50 separate launches; 'auto' (default) = "
+                         "graph when the capture succeeds (it cannot with a CPU-resident learnable temperature: c4), else eager")
+    ap.add_argument("--graph", action="store_true", help="same as --launch graph")
     a = ap.parse_args()
+    if a.graph:
+        a.launch = "graph"
     cfg = CONFIGS[a.config]
     a.batch = a.batch or cfg["batch"]
     a.dim = a.dim or cfg["dim"]
@@ -352,28 +357,42 @@ def run_ours(args):
             break
     barrier()
 
-    # The whole step (about 55 launches, most of them tiny) is captured once into a CUDA graph and replayed: the
-    # library is capturable by contract (no allocation, no host sync, caller's stream).  Collectives stay eager.
+    # The whole step (about 50 launches, most of them tiny, plus the NCCL collectives at N > 1) is captured once into a
+    # CUDA graph and replayed: the library is capturable by contract (no allocation, no host sync, caller's stream).
+    # A learnable temperature living on the CPU (the reference's placement, sparsify_clip.py:716-717) needs a device-to-host
+    # copy of its gradient every step, which a capture cannot contain: that configuration runs eager.
     graphed = None
-    if args.graph and world == 1:
+    # 'auto': graph on one GPU; eager at N > 1 (measured at N = 2: 4.30 ms replayed vs 4.22 ms eager -- the step is
+    # kernel-bound and the collectives already run asynchronously under the sweeps)
+    want_graph = args.launch == "graph" or (args.launch == "auto" and not cfg["learn_tau"] and world == 1)
+    ok_flag = torch.ones(1, device=dev, dtype=torch.int32)
+    if want_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 step(I, T)
             torch.cuda.current_stream().wait_stream(side)
+            barrier()
             gr = torch.cuda.CUDAGraph()
             I.grad = None
             T.grad = None
-            with torch.cuda.graph(gr):
+            # thread_local: the NCCL watchdog thread's own CUDA calls must not invalidate this thread's capture
+            with torch.cuda.graph(gr, capture_error_mode="thread_local"):
                 g_loss = scb.weighted_loss(I, T, tau_p, W, group=group)
                 g_loss.backward()
             graphed = (gr, g_loss)
             gr.replay()
             torch.cuda.synchronize()
         except Exception as exc:      # fall back to eager timing, and say so
-            sys.stderr.write(f"bench.py: CUDA-graph capture failed ({exc}); timing eager launches\n")
+            sys.stderr.write(f"bench.py[rank {rank}]: CUDA-graph capture failed ({type(exc).__name__}: {exc}); timing eager launches\n")
             graphed = None
+            ok_flag.zero_()
+        if world > 1:                 # every rank replays, or none does
+            dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN)
+            if ok_flag.item() == 0:
+                graphed = None
+        barrier()
 
     def timed_step():
         if graphed is None:
@@ -474,11 +493,42 @@ def run_ours(args):
 
     def prefetch(k):
         bsel = k & 1
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(copy_stream), torch.no_grad():
             copy_stream.wait_event(ev_free[bsel])          # the step that last read this buffer has finished
             dbuf[bsel][0].copy_(hI, non_blocking=True)
             dbuf[bsel][1].copy_(hT, non_blocking=True)
             ev_in[bsel].record(copy_stream)
+
+    # with graph launches: one captured step per device buffer pair (the graph reads fixed addresses)
+    e2e_graphs = None
+    if graphed is not None:
+        try:
+            e2e_graphs = []
+            for bsel in range(2):
+                Iv = dbuf[bsel][0].requires_grad_(True)
+                Tv = dbuf[bsel][1].requires_grad_(True)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    step(Iv, Tv)
+                torch.cuda.current_stream().wait_stream(side)
+                barrier()
+                Iv.grad = None
+                Tv.grad = None
+                gre = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gre, capture_error_mode="thread_local"):
+                    le = scb.weighted_loss(Iv, Tv, tau_p, W, group=group)
+                    le.backward()
+                e2e_graphs.append((gre, le))
+        except Exception as exc:
+            sys.stderr.write(f"bench.py[rank {rank}]: e2e graph capture failed ({type(exc).__name__}: {exc}); e2e runs eager\n")
+            e2e_graphs = None
+            ok_flag.zero_()
+        if world > 1:
+            dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN)
+            if ok_flag.item() == 0:
+                e2e_graphs = None
+        barrier()
 
     def e2e_run(ksteps):
         cur = torch.cuda.current_stream()
@@ -489,9 +539,13 @@ def run_ours(args):
             if k + 1 < ksteps:
                 prefetch(k + 1)
             cur.wait_event(ev_in[k & 1])
-            Iv = dbuf[k & 1][0].detach().requires_grad_(True)
-            Tv = dbuf[k & 1][1].detach().requires_grad_(True)
-            l = step(Iv, Tv)
+            if e2e_graphs is not None:
+                e2e_graphs[k & 1][0].replay()
+                l = e2e_graphs[k & 1][1]
+            else:
+                Iv = dbuf[k & 1][0].detach().requires_grad_(True)
+                Tv = dbuf[k & 1][1].detach().requires_grad_(True)
+                l = step(Iv, Tv)
             ev_free[k & 1].record(cur)
             hloss.copy_(l.detach(), non_blocking=True)
 
@@ -542,6 +596,7 @@ def run_ours(args):
             "peak_device_memory_bytes_rank0": int(peak_mem),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * D * 2, "d2h_bytes_per_step": 4,
                     "ms_per_step": et.item(),
+                    "launch": "one CUDA-graph replay per step" if e2e_graphs is not None else "eager launches",
                     "how": "public API on device buffers filled from pinned host memory; the copy of step k+1 overlaps "
                            "the compute of step k (double buffer, copy stream); one CUDA-event region over all steps. "
                            "Only the 4-byte loss is read back: the gradients dI, dT stay on the device, where the training "
@@ -567,8 +622,14 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_record(args)
         print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: destroying a process group whose collectives were captured into
+        # CUDA graphs was measured to hang (the line above is already out), and nothing is left to clean up.
+        graphed = e2e_graphs = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -232,8 +232,11 @@ class _FusedTermsFn(torch.autograd.Function):
         dev = Ip.device
         need_I, need_T, need_tau = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         need = need_I or need_T
-        # ---- exchange step 1: the operands (both gathers in flight together)
-        I_all, T_all, pending = Ip, Tp, []
+        # ---- exchange step 1: the operands.  Every gather is asynchronous (NCCL's own stream) and is awaited right
+        # before the first sweep that reads its result, so the later gathers run UNDER the earlier sweeps: the gradient
+        # sweeps occupy clusters of 4 SMs (132 of a B200's 148 SMs), which leaves room for the small NCCL kernels.
+        I_all, T_all = Ip, Tp
+        hI = hT = hC = None
         # normalised centroids (sparsify_clip.py:353 + :804): fp32 master copy C, tensor-core operand Cq (see
         # centroid_operand_dtype: fp16 keeps the term inside the parity gates where bf16 does not)
         C = Cq = C_all = c_inv = None
@@ -244,30 +247,42 @@ class _FusedTermsFn(torch.autograd.Function):
             C_all = Cq
         if group is not None:
             if w_a != 0.0 or w_i != 0.0:
-                I_all, h = _all_gather_rows_async(Ip, group)
-                pending.append(h)
+                I_all, hI = _all_gather_rows_async(Ip, group)
             if w_a != 0.0 or w_t != 0.0:
-                T_all, h = _all_gather_rows_async(Tp, group)
-                pending.append(h)
+                T_all, hT = _all_gather_rows_async(Tp, group)
             if w_c != 0.0:
-                C_all, h = _all_gather_rows_async(Cq, group)
-                pending.append(h)
+                C_all, hC = _all_gather_rows_async(Cq, group)
+
+        def _await(h):
+            if h is not None:
+                h.wait()
+            return None
+
         # scalar partial sums of this rank, written in place by the kernels that produce them:
-        #   0: sum r   1: sum c   2: sum diag   3: L_align   4, 5, 6: L_unif row sums (I, T, centroids)   7: d/dtau
-        NS = 7                                               # how many of them travel in the packed gather
+        #   0: sum r   1: sum c   2: sum diag   3: L_align   4: L_unif row sum (I)   |   5, 6: L_unif row sums (T, centroids)
+        #   7: d/dtau.   Sharded: 0..4 travel in the packed gather (exchange step 2), 5..7 in the late all-reduce (step 3).
+        NS, NP = 7, 5
         parts = torch.zeros(NS + 1, dtype=torch.float32, device=dev)
         if w_l != 0.0:
             be.sum(be.lalign_rows(Ip, Tp), out=parts[3:4])
-        for h in pending:
-            h.wait()
+        cores = {}
+
+        def _unif(wu, Xp, X_all, needx, which, slot):
+            if wu != 0.0:
+                core = be.lunif_core(Xp, X_all, float(t_unif), off, needx, sum_out=parts[slot:slot + 1])
+                cores[which] = (core, wu, needx, slot - 4)
+
+        # L_unif(I) needs only the gathered I: it runs while T (and the centroids) are still in flight
+        hI = _await(hI)
+        _unif(w_i, Ip, I_all, need_I, "I", 4)
         an_I = an_T = None
         scale = 0.0
         r = c = None
-        # every B x B sweep that does not need the other ranks' statistics first: LSE and L_unif
+        colparts = None
         if w_a != 0.0:
+            hT = _await(hT)
             tau = float(tau_t) if tau_t is not None else float(tau_f)
             scale = 1.0 / tau
-            colparts = None
             if group is None:
                 r, c = be.lse_rows_cols(Ip, Tp, scale)      # both from one sweep over S
             else:
@@ -282,61 +297,70 @@ class _FusedTermsFn(torch.autograd.Function):
             be.sum(diag, out=parts[2:3])
             if colparts is None:
                 be.sum(c, out=parts[1:2])
-        un_I = un_T = None
-        cores = {}
-        for (wu, Xp, X_all, needx, which, slot) in ((w_i, Ip, I_all, need_I, "I", 4), (w_t, Tp, T_all, need_T, "T", 5),
-                                                    (w_c, Cq, C_all, need, "C", 6)):
-            if wu == 0.0:
-                continue
-            core = be.lunif_core(Xp, X_all, float(t_unif), off, needx, sum_out=parts[slot:slot + 1])
-            cores[which] = (core, wu, needx, slot - 4)
-        # ---- exchange step 2: ONE small gather carries r, c and the scalar partials of every rank.  It is issued
-        # between sweeps, not under one: an NCCL kernel that shares the SMs with a persistent sweep slows the sweep
-        # more than the overlap saves (measured at 8 GPUs).
+        # ---- exchange step 2: ONE small gather carries r, c (or the column partials) and the scalar partials 0..4 of
+        # every rank; it is issued here and awaited after the remaining L_unif sweeps, i.e. it runs under them.
         r_all, c_all = r, c
         gathered = False
+        hP = pack_flat = None
         if group is not None and w_a != 0.0 and (need or need_tau or colparts is not None):
             if colparts is None:
-                pieces = (r, c, parts[:NS])
+                pieces = (r, c, parts[:NP])
             else:
                 _, cM, cL, c_exact, flag = colparts
-                pieces = (r, c_exact, parts[:NS], cM, cL)
+                pieces = (r, c_exact, parts[:NP], cM, cL)
             pack = torch.cat([x.to(torch.float32) for x in pieces])
             pack_flat = torch.empty(ws * pack.numel(), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(pack_flat, pack, group=group)
+            hP = dist.all_gather_into_tensor(pack_flat, pack, group=group, async_op=True)
+            gathered = True
+        hT = _await(hT)
+        _unif(w_t, Tp, T_all, need_T, "T", 5)
+        hC = _await(hC)
+        _unif(w_c, Cq, C_all, need, "C", 6)
+        local_sdiag = parts[2].clone() if (gathered and need_tau) else parts[2]
+        if gathered:
+            hP = _await(hP)
             pack_all = pack_flat.view(ws, -1)
             r_all = pack_all[:, :n].reshape(-1)
-            local_sdiag = parts[2].clone() if need_tau else None
-            parts = torch.cat((pack_all[:, 2 * n:2 * n + NS].sum(0), parts[NS:]))
+            parts = torch.cat((pack_all[:, 2 * n:2 * n + NP].sum(0), parts[NP:]))
             if colparts is None:
                 c_all = pack_all[:, n:2 * n].reshape(-1)
             else:
                 # fold the column partials of all ranks (or take the exact second sweep where the bound demanded it)
-                c_all = be.lse2_fold_ranks(pack_all, n, n, 2 * n + NS, 2 * n + NS + B, flag)
+                c_all = be.lse2_fold_ranks(pack_all, n, n, 2 * n + NP, 2 * n + NP + B, flag)
                 c = c_all[off:off + n]
                 be.sum(c_all, out=parts[1:2])
-            gathered = True
-        else:
-            local_sdiag = parts[2]
+        # ---- exchange step 3 (what step 2 could not carry: the L_unif sums produced under it, later d/dtau; everything
+        # when there is no anchor term).  L_unif-only compositions reduce here, before the gradient coefficients are formed.
+        hR = hD = None
+        late_lo = NP if gathered else 0
+        if group is not None and not (w_a != 0.0 and (need_I or need_tau or need_T)):
+            if (not gathered) or w_t != 0.0 or w_c != 0.0:
+                dist.all_reduce(parts[late_lo:NS], group=group)
         if w_a != 0.0 and (need or need_tau):
             coef = w_a * scale / (2.0 * B)
+            if group is not None and (not gathered or w_t != 0.0 or w_c != 0.0):
+                late = parts[late_lo:NS].clone()             # reduced under the anchor-gradient sweeps
+                hR = dist.all_reduce(late, group=group, async_op=True)
             if need_I or need_tau:
                 p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
                 an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef)
                 if need_tau:
                     parts[NS] = p["ws"] - 2.0 * local_sdiag
+                    if group is not None:                    # reduced under the dT sweep
+                        dtau_part = parts[NS:].clone()
+                        hD = dist.all_reduce(dtau_part, group=group, async_op=True)
             if need_T:
                 p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
                 an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
-        # ---- exchange step 3 (only what step 2 did not carry): d/dtau, or everything when there is no anchor term
-        if group is not None:
-            if not gathered:
-                _all_reduce_(parts, group)
-            elif need_tau:
-                _all_reduce_(parts[NS:], group)
+            if hR is not None:
+                hR = _await(hR)
+                parts[late_lo:NS] = late
+            if hD is not None:
+                hD = _await(hD)
+                parts[NS:] = dtau_part
         # the additions of the ladder on the (now global) partial sums, and 1 / Ssum of every L_unif term, in one launch
         loss, inv_ssum = be.loss_assemble(parts, w_a / (2.0 * B), 2.0 * scale, w_l / B, w_i, w_t, w_c, B * (B - 1) / 2.0)
-        cen = None
+        cen = un_I = un_T = None
         for which, (core, wu, needx, k) in cores.items():
             if needx:
                 u = dict(core=core, coef=wu * (-2.0 * float(t_unif)), dev_coef=inv_ssum[k:k + 1])
