@@ -362,9 +362,9 @@ def run_ours(args):
     # A learnable temperature living on the CPU (the reference's placement, sparsify_clip.py:716-717) needs a device-to-host
     # copy of its gradient every step, which a capture cannot contain: that configuration runs eager.
     graphed = None
-    # 'auto': graph on one GPU; eager at N > 1 (measured at N = 2: 4.30 ms replayed vs 4.22 ms eager -- the step is
-    # kernel-bound and the collectives already run asynchronously under the sweeps)
-    want_graph = args.launch == "graph" or (args.launch == "auto" and not cfg["learn_tau"] and world == 1)
+    # measured (profiles/r02l_*): N = 8 1.27 ms replayed vs 1.33 ms eager (the shard step is ~50 launches for ~1.1 ms of
+    # sweeps); N = 2 and N = 1 within noise of each other
+    want_graph = args.launch == "graph" or (args.launch == "auto" and not cfg["learn_tau"])
     ok_flag = torch.ones(1, device=dev, dtype=torch.int32)
     if want_graph:
         try:
