@@ -213,6 +213,34 @@ int scb_loss_assemble(const float* parts, float c_anchor, float two_scale, float
 int scb_sparsify_sum_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
                           int dtype, int64_t row_offset, int jparts, float* rs, int path, void* stream);
 
+/* ------------------------------------------------------------------ cold variants and evaluation-side consumers */
+
+/* out[d] = scale * sum_i (X[i,d] - Y[i,d])   (Y may be NULL).  centroid_alignment_loss (sparsify_clip.py:487-505) and
+ * compute_gap (:418-436) are |mean I - mean T|_p; the mean off-diagonal cosine (:438-457) is
+ * (|sum_i x_i|^2 - sum_i |x_i|^2) / (N (N - 1)).  scratch: [scratch_rows][D] fp32, scratch_rows >= 1 (more rows = more
+ * parallelism; fixed-order two-stage sum). */
+int scb_col_sum(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype, float scale,
+                float* scratch, int scratch_rows, float* out, void* stream);
+/* out[D][D] = scale * sum_i (x_i - mu)(x_i - mu)^T   (mu may be NULL), fp32 FMA.  The covariance of the W2 uniformity
+ * metric (uniformity.py:26, :70, :106, :150, :188; sparsify_clip.py:466) and X^T X of sparsify_loss's backward.
+ * scratch: [scratch_parts][D][D] fp32. */
+int scb_gram_dd(const void* X, int64_t n, int D, int64_t ld, int dtype, const float* mu, float scale, float* scratch,
+                int scratch_parts, float* out, void* stream);
+/* out[n][D] (fp32, contiguous) = X[n][D] . M[D][D] */
+int scb_rows_times_dd(const void* X, int64_t n, int D, int64_t ld, int dtype, const float* M, float* out, void* stream);
+/* out[i] = scale * sum_p parts[p][i], fixed order */
+int scb_sum_parts(const float* parts, int nparts, int64_t n, float scale, float* out, void* stream);
+/* rank[q] = #{e : S[l, e] > S[l, gt[q]]}, l = line ? line[q] : q, for n_lines queries over the lines of a score matrix
+ * given with explicit strides (rows: stride_line = ld, stride_elem = 1; columns: the transpose): the position of the
+ * ground truth in the descending sort of compute_metric_ret (sparsify_clip.py:374-378, :396-400). */
+int scb_rank_count(const void* S, int64_t n_lines, int64_t n_elem, int64_t stride_line, int64_t stride_elem, int dtype,
+                   const int64_t* line, const int64_t* gt, int* rank, void* stream);
+/* The same rank from the FEATURES: cnt[part*nsub + s][i] partial counts of #{j != i + diag_off : A_i . Bm_j > gt_score[i]}
+ * (sum them with scb_sum_parts); the N x N similarity of sparsify_clip.py:628 is produced tile by tile and never stored.
+ * jparts / nsub from scb_pass_plan(path, nA, nB, D, grad = 0, ...). */
+int scb_rank_count_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                        const float* gt_score, int64_t diag_off, int jparts, float* cnt, int path, void* stream);
+
 /* debug: device buffer of 2 x 4 x 4096 x 2 uint64 that the CTA-pair kernel fills with a per-role timeline of
  * cluster 0 (tag, tile, clock64) on the following launches; NULL switches it off (tools/pair_trace.py). */
 int scb_debug_pair_trace(void* buf);

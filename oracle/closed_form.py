@@ -260,3 +260,56 @@ def weighted_loss(I, T, tau, w_anchor, w_align, w_ui, w_ut, w_uc, t=2):
 def compose_loss(config, I, T, tau, epoch=0, current_batch=1, t_total=100):
     w = ladder_terms(config, epoch, current_batch, t_total)
     return weighted_loss(I, T, tau, *w)
+
+
+# ----------------------------------------------------------------------------
+# evaluation-side consumers -- sparsify_clip.py:357-528 (numpy restatements; ranks through a full descending sort,
+# like the reference)
+# ----------------------------------------------------------------------------
+def retrieval_ranks(score_matrix, ids, ids_txt):
+    """(forward ranks [N_text], backward ranks [N_image]) as compute_metric_ret computes them (:374-378, :396-400)."""
+    S = _f64(score_matrix)
+    order_r = np.argsort(-S, axis=1, kind="stable")
+    fwd = []
+    for i in range(len(ids_txt)):
+        gt = ids.index(ids_txt[i])
+        fwd.append(int(np.where(order_r[i] == gt)[0][0]))
+    order_c = np.argsort(-S, axis=0, kind="stable").T
+    bwd = []
+    for i in range(len(ids)):
+        gts = [k for k, t in enumerate(ids_txt) if t == ids[i]]
+        bwd.append(min(int(np.where(order_c[i] == g)[0][0]) for g in gts))
+    return np.array(fwd), np.array(bwd)
+
+
+def recall_log(rank, prefix):
+    n = len(rank)
+    r1, r5, r10 = (rank < 1).sum() / n, (rank < 5).sum() / n, (rank < 10).sum() / n
+    return {f"{prefix}_r1": round(r1 * 100, 4), f"{prefix}_r5": round(r5 * 100, 4), f"{prefix}_r10": round(r10 * 100, 4),
+            f"{prefix}_ravg": round((r1 + r5 + r10) / 3 * 100, 4)}
+
+
+def compute_gap(f1, f2):                                   # :418-436
+    return float(np.linalg.norm(np.mean(_f64(f1), axis=0) - np.mean(_f64(f2), axis=0)))
+
+
+def mean_angular_value(f):                                 # :438-457
+    X = _f64(f)
+    G = X @ X.T
+    n = X.shape[0]
+    return float((G.sum() - np.trace(G)) / (n * (n - 1)))
+
+
+def mean_true_pair_cosine(f1, f2):                         # :508-528
+    return float(np.mean(np.sum(_f64(f1) * _f64(f2), axis=1)))
+
+
+def w2_uniformity(f1, f2, eps=1e-8):                       # :459-485 / uniformity.py:101-128 (returns -W2)
+    x = np.concatenate([_f64(f1), _f64(f2)], axis=0)
+    n, dim = x.shape
+    mu = x.mean(axis=0)
+    xc = x - mu
+    cov = xc.T @ xc / n
+    lam = np.linalg.eigvalsh(cov)
+    tr_sqrt = np.sqrt(np.clip(lam + eps, 0, None)).sum()
+    return -float(np.sqrt(np.sum(mu * mu) + 1.0 + np.trace(cov) - 2.0 / np.sqrt(dim) * tr_sqrt))

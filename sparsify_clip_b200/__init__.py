@@ -13,6 +13,8 @@ from .losses import (centroid_alignment_loss, compute_centroids, compute_centroi
                      contrastive_loss_roberta, fused_terms_loss, l2_normalize, lalign_loss, lunif_loss, normalized_centroids, operand_dtype, centroid_operand_dtype,
                      random_alignment_loss, sparsify_loss)
 
+from . import metrics  # noqa: E402  (evaluation-side consumers: sparsify_clip.py:357-528)
+
 _lib.load()   # fail loudly at import time: there is no CPU fallback
 
 __all__ = [

@@ -50,6 +50,12 @@ SIGNATURES = {
     "scb_grad_combine": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i32, _vp, _i32,
                          _f32, _vp, _f32, _vp, _f32, _vp, _vp, _i32, _i64, _vp],
     "scb_sparsify_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _i64, _i32, _vp, _i32, _vp],
+    "scb_col_sum": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _i32, _vp, _vp],
+    "scb_gram_dd": [_vp, _i64, _i32, _i64, _i32, _vp, _f32, _vp, _i32, _vp, _vp],
+    "scb_rows_times_dd": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp],
+    "scb_sum_parts": [_vp, _i32, _i64, _f32, _vp, _vp],
+    "scb_rank_count": [_vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp],
+    "scb_rank_count_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _vp],
 }
 
 _lib = None

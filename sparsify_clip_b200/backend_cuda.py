@@ -514,6 +514,78 @@ class CudaBackend:
         return self.sum(rs)
 
 
+    # ------------------------------------------------------------------ cold variants / evaluation-side consumers
+    def col_sum(self, X, Y=None, scale=1.0):
+        """scale * sum_i (X[i] - Y[i]) -> [D] fp32 (Y optional)."""
+        n, D = X.shape
+        rows = max(1, min(256, (n + 127) // 128))
+        scratch = _empty(rows, D, dtype=torch.float32, device=X.device)
+        out = _empty(D, dtype=torch.float32, device=X.device)
+        with _On(X.device):
+            check(self.lib.scb_col_sum(_ptr(X), _ptr(Y), n, D, X.stride(0), Y.stride(0) if Y is not None else 0, _DT[X.dtype],
+                                       float(scale), _ptr(scratch), rows, _ptr(out), self._stream()), "col_sum")
+        self._count(2)
+        return out
+
+    def gram_dd(self, X, mu=None, scale=1.0):
+        """scale * sum_i (x_i - mu)(x_i - mu)^T -> [D, D] fp32."""
+        n, D = X.shape
+        parts = max(1, min(64, (n + 511) // 512))
+        scratch = _empty(parts, D, D, dtype=torch.float32, device=X.device)
+        out = _empty(D, D, dtype=torch.float32, device=X.device)
+        with _On(X.device):
+            check(self.lib.scb_gram_dd(_ptr(X), n, D, X.stride(0), _DT[X.dtype], _ptr(mu), float(scale), _ptr(scratch), parts,
+                                       _ptr(out), self._stream()), "gram_dd")
+        self._count(2)
+        return out
+
+    def rows_times_dd(self, X, M):
+        n, D = X.shape
+        assert M.dtype == torch.float32 and M.is_contiguous() and M.shape == (D, D)
+        out = _empty(n, D, dtype=torch.float32, device=X.device)
+        with _On(X.device):
+            check(self.lib.scb_rows_times_dd(_ptr(X), n, D, X.stride(0), _DT[X.dtype], _ptr(M), _ptr(out), self._stream()),
+                  "rows_times_dd")
+        self._count()
+        return out
+
+    def sum_parts(self, parts, scale=1.0):
+        """[P, n] fp32 -> [n]: fixed-order sum over the partial slots."""
+        P, n = parts.shape
+        out = _empty(n, dtype=torch.float32, device=parts.device)
+        with _On(parts.device):
+            check(self.lib.scb_sum_parts(_ptr(parts), P, n, float(scale), _ptr(out), self._stream()), "sum_parts")
+        self._count()
+        return out
+
+    def rank_count(self, S, gt, columns=False, line=None):
+        """Position of S[l, gt] in the descending sort of line l (row, or column when `columns`) -> int32 [len(gt)]."""
+        assert S.dim() == 2 and S.stride(1) == 1 and gt.dtype == torch.int64
+        n_r, n_c = S.shape
+        nq = gt.numel()
+        out = _empty(nq, dtype=torch.int32, device=S.device)
+        sl, se, ne = (1, S.stride(0), n_r) if columns else (S.stride(0), 1, n_c)
+        with _On(S.device):
+            check(self.lib.scb_rank_count(_ptr(S), nq, ne, sl, se, _DT[S.dtype], _ptr(line), _ptr(gt), _ptr(out),
+                                          self._stream()), "rank_count")
+        self._count()
+        return out
+
+    def rank_count_pass(self, A, Bm, gt_score, diag_off=0):
+        """#{j != i + diag_off : A_i . Bm_j > gt_score[i]} per row of A, from the features -> fp32 [nA] (exact integers)."""
+        nA, D = A.shape
+        nB = Bm.shape[0]
+        path = self.path_for(A, Bm)
+        jp, nsub = self._plan(path, nA, nB, D, False, A.device)
+        cnt = _empty(jp * nsub, nA, dtype=torch.float32, device=A.device)
+        with _On(A.device):
+            check(self.lib.scb_rank_count_pass(_ptr(A), nA, _ptr(Bm), nB, D, A.stride(0), Bm.stride(0), _DT[A.dtype],
+                                               _ptr(gt_score), int(diag_off), jp, _ptr(cnt), path, self._stream()),
+                  "rank_count_pass")
+        self._count()
+        return self.sum_parts(cnt)
+
+
 _backend = None
 
 

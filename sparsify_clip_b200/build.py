@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # SCB_LIB_SUFFIX / SCB_EXTRA_FLAGS (tuning experiments): build a variant library next to the shipped one
 LIB = os.path.join(HERE, "libscb200" + os.environ.get("SCB_LIB_SUFFIX", "") + ".so")
-SOURCES = ["rowwise.cu", "simt_pass.cu", "tc_pass.cu", "tc_pair.cu", "tc_quad.cu", "api.cu"]
+SOURCES = ["rowwise.cu", "simt_pass.cu", "tc_pass.cu", "tc_pair.cu", "tc_quad.cu", "metrics.cu", "api.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "scb200.h")]
 # no --use_fast_math: the SIMT path is the exact fp32 path (expf/exp2f/division must stay IEEE-accurate)
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

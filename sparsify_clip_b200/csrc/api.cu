@@ -17,6 +17,10 @@ int scb_tc_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t,
 int scb_tc_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*, int64_t,
                  int, float*, float*, float*, cudaStream_t);
 int scb_tc_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
+int scb_simt_rank_count(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, const float*, int64_t, int, float*,
+                        cudaStream_t);
+int scb_tc_rank_count(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, const float*, int64_t, int, float*,
+                      cudaStream_t);
 int scb_tc_set_flags(int);
 int scb_tc_grad_kernel(int64_t nA, int D, int grad);
 int scb_quad_clusters();
@@ -158,4 +162,17 @@ extern "C" int scb_sparsify_sum_pass(const void* Xr, int64_t nR, const void* Xal
   cudaStream_t s = (cudaStream_t)stream;
   return path == SCB_PATH_TC ? scb_tc_sparsify_sum(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, row_offset, jparts, rs, s)
                              : scb_simt_sparsify_sum(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, row_offset, jparts, rs, s);
+}
+
+// cnt[part][i] = #{j != i + diag_off : A_i . Bm_j > gt_score[i]}: the rank of row i's ground-truth pair among the columns,
+// from the features (the N x N score matrix of sparsify_clip.py:628 is never materialised)
+extern "C" int scb_rank_count_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
+                                   int dtype, const float* gt_score, int64_t diag_off, int jparts, float* cnt, int path,
+                                   void* stream) {
+  SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path);
+  SCB_CHECK_ARG((gt_score && cnt) || nA == 0, SCB_E_ARG, "rank_count_pass: null argument");
+  SCB_CHECK_ARG(nB > 0, SCB_E_ARG, "rank_count_pass: empty column side");
+  cudaStream_t s = (cudaStream_t)stream;
+  return path == SCB_PATH_TC ? scb_tc_rank_count(A, nA, Bm, nB, D, ldA, ldB, dtype, gt_score, diag_off, jparts, cnt, s)
+                             : scb_simt_rank_count(A, nA, Bm, nB, D, ldA, ldB, dtype, gt_score, diag_off, jparts, cnt, s);
 }

@@ -11,7 +11,7 @@
 
 namespace {
 
-enum { M_LSE = 0, M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2, M_LUNIF_SUM = 3, M_SPARSIFY_SUM = 4 };
+enum { M_LSE = 0, M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2, M_LUNIF_SUM = 3, M_SPARSIFY_SUM = 4, M_RANK_COUNT = 6 };
 
 constexpr int TR = 32;    // rows per CTA
 constexpr int TJ = 32;    // columns of S per tile
@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) k_simt_pass(const SimtParams P) {
     rowc[rr] = 0.f;
     if (MODE == M_ANCHOR_GRAD) rowc[rr] = ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
     if (MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM) rowc[rr] = ok ? P.rowvec[gi] : 0.f;
+    if (MODE == M_RANK_COUNT) rowc[rr] = ok ? P.rowvec[gi] : INFINITY;
     st0[rr] = (MODE == M_LSE) ? -INFINITY : 0.f;
     st1[rr] = 0.f;
   }
@@ -118,6 +119,8 @@ __global__ void __launch_bounds__(256) k_simt_pass(const SimtParams P) {
         st0[rr] += s;
         st1[rr] += s;
         w[rr] = ww;
+      } else if (MODE == M_RANK_COUNT) {
+        st0[rr] += scb_warp_sum((jok && !is_diag && g > rowc[rr]) ? 1.f : 0.f);
       } else {  // M_SPARSIFY_SUM
         const float e = g - (is_diag ? 1.f : -1.f);
         st0[rr] += scb_warp_sum(jok ? e * e : 0.f);
@@ -198,6 +201,11 @@ int scb_simt_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, i
                    float* rq, float* rs, cudaStream_t s) {
   SimtParams P{Xr, Xall, nR, nAll, ldR, ldAll, D, dtype, jparts, t * SCB_LOG2E, sqn_r, sqn_all, row_offset, U, rq, rs};
   return U ? launch<M_LUNIF_GRAD>(P, s) : launch<M_LUNIF_SUM>(P, s);
+}
+int scb_simt_rank_count(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                        const float* gt_score, int64_t diag_off, int jparts, float* cnt, cudaStream_t s) {
+  SimtParams P{A, Bm, nA, nB, ldA, ldB, D, dtype, jparts, 0.f, gt_score, nullptr, diag_off, nullptr, cnt, nullptr};
+  return launch<M_RANK_COUNT>(P, s);
 }
 int scb_simt_sparsify_sum(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
                           int dtype, int64_t row_offset, int jparts, float* rs, cudaStream_t s) {

@@ -25,7 +25,7 @@
 
 namespace {
 
-enum { M_LSE = 0, M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2, M_LUNIF_SUM = 3, M_SPARSIFY_SUM = 4, M_LSE2 = 5 };
+enum { M_LSE = 0, M_ANCHOR_GRAD = 1, M_LUNIF_GRAD = 2, M_LUNIF_SUM = 3, M_SPARSIFY_SUM = 4, M_LSE2 = 5, M_RANK_COUNT = 6 };
 // M_LSE2: row LSE as M_LSE plus, from the SAME S tiles, per-(row block, column) partial column sums
 //   colsum[strip][j] * 2^colref[strip][j/32] = sum_{i in 32-row strip} 2^{y_ij}   (y = scale*log2e * a_i.b_j)
 // so that the column LSE needs no second sweep over S^T.  Exact while the spread of y inside a 32 x 32 block stays
@@ -331,6 +331,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       float rowc = 0.f;
       if (MODE == M_ANCHOR_GRAD) rowc = row_ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
       if (MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM) rowc = row_ok ? P.rowvec[gi] * P.p0 : 0.f;
+      if (MODE == M_RANK_COUNT) rowc = row_ok ? P.rowvec[gi] : INFINITY;      // the score of the row's ground-truth pair
       float st0 = (MODE == M_LSE || MODE == M_LSE2) ? -INFINITY : 0.f, st1 = 0.f;
       const int64_t my_diag_col = gi + P.diag_off;  // column index that is "the diagonal" of this row
 
@@ -420,6 +421,11 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int64_t prow = (int64_t)rb * 4 + q;
             if (cbase + lane < P.nB) P.c1[prow * P.nB + cbase + lane] = ef[0];
             if (lane == 0 && cbase < P.nB) P.c0[prow * ((P.nB + 31) / 32) + (cbase >> 5)] = rho - kColBias;
+          } else if (MODE == M_RANK_COUNT) {
+            // how many scores of this row beat its ground-truth score (dead columns hold -1e30; the ground-truth
+            // column itself never counts, whatever the last bits of its recomputed score)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) st0 += (__uint_as_float(v[c]) > rowc && c != dcol) ? 1.f : 0.f;
           } else if (MODE == M_SPARSIFY_SUM) {
             if (!tile_partial && !diag_here) {
 #pragma unroll
@@ -537,7 +543,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
         if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
         if (MODE == M_LUNIF_SUM) P.s1[o] = st1;
-        if (MODE == M_SPARSIFY_SUM) P.s0[o] = st0;
+        if (MODE == M_SPARSIFY_SUM || MODE == M_RANK_COUNT) P.s0[o] = st0;
       }
     }  // items
   }
@@ -706,6 +712,12 @@ int scb_tc_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int
   P.out = U; P.s0 = rq; P.s1 = rs;
   return U ? launch_tc<M_LUNIF_GRAD>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s)
            : launch_tc<M_LUNIF_SUM>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
+}
+int scb_tc_rank_count(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                      const float* gt_score, int64_t diag_off, int jparts, float* cnt, cudaStream_t s) {
+  TcParams P{};
+  P.jparts = jparts; P.rowvec = gt_score; P.diag_off = diag_off; P.s0 = cnt;
+  return launch_tc<M_RANK_COUNT>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
 }
 int scb_tc_sparsify_sum(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
                         int dtype, int64_t row_offset, int jparts, float* rs, cudaStream_t s) {

@@ -531,24 +531,28 @@ def compute_centroids(text_embeddings, visual_embeddings):
 
 # ----------------------------------------------------------------------------- cold variants
 class _SparsifyFn(torch.autograd.Function):
-    """mse(x x^T, 2 eye - 1) -- sparsify_clip.py:166-176.  Forward on the Gram-tile kernel;
-    backward (4/B^2)(E X) stays in PyTorch (cold path: no YAML selects this loss)."""
+    """mse(x x^T, 2 eye - 1) -- sparsify_clip.py:166-176.  Forward on the Gram-tile sweep; backward without a second
+    B x B pass: with E = X X^T + 1 1^T - 2 I,  dX = (4 / B^2) E X = (4 / B^2) (X (X^T X) + 1 (sum_j x_j)^T - 2 X), i.e. one
+    D x D second moment (scb_gram_dd) and one [B, D] x [D, D] product (scb_rows_times_dd) of the SAME prepared operand."""
 
     @staticmethod
     def forward(ctx, x):
         be = get_backend()
         xp = be.prep(x)
         B = xp.shape[0]
-        ctx.save_for_backward(x)
+        ctx.save_for_backward(xp)
+        ctx.in_dtype = x.dtype
         return be.sparsify_sum(xp, xp, 0) / float(B * B)
 
     @staticmethod
     def backward(ctx, gout):
-        (x,) = ctx.saved_tensors
-        xf = x.detach().float()
-        B = xf.shape[0]
-        E = xf @ xf.t() - (2.0 * torch.eye(B, device=xf.device) - 1.0)
-        return ((4.0 / (B * B)) * (E @ xf) * _gout32(gout)).to(x.dtype)
+        be = get_backend()
+        (xp,) = ctx.saved_tensors
+        B = xp.shape[0]
+        XM = be.rows_times_dd(xp, be.gram_dd(xp))
+        s = be.col_sum(xp)
+        g = (XM + s[None, :] - 2.0 * xp.float()) * ((4.0 / (B * B)) * _gout32(gout))
+        return g.to(ctx.in_dtype)
 
 
 def sparsify_loss(x):
@@ -570,6 +574,37 @@ def contrastive_loss_roberta(image_embeds, text_embeds, roberta_similarity, temp
     return (li + lt) / 2
 
 
+class _CentroidAlignFn(torch.autograd.Function):
+    """|| mean(img) - mean(txt) ||_p -- sparsify_clip.py:487-505: one column-sum kernel over the rows (scb_col_sum); the
+    p-norm of the D-vector and its gradient sign(d) |d|^(p-1) / |d|_p^(p-1) / B are O(D)."""
+
+    @staticmethod
+    def forward(ctx, a, b, p):
+        be = get_backend()
+        a, b = _common(a, b)
+        ap, bp = be.prep(a), be.prep(b)
+        n = ap.shape[0]
+        d = be.col_sum(ap, bp, 1.0 / n)
+        nrm = torch.linalg.vector_norm(d, ord=p)
+        ctx.save_for_backward(d, nrm)
+        ctx.meta = (p, n, a.shape, a.dtype, b.dtype)
+        return nrm
+
+    @staticmethod
+    def backward(ctx, gout):
+        d, nrm = ctx.saved_tensors
+        p, n, shape, dta, dtb = ctx.meta
+        if p == 2:
+            gd = d / nrm
+        else:
+            gd = torch.sign(d) * d.abs().pow(p - 1) / nrm.pow(p - 1)
+        row = (gd * (_gout32(gout) / n))[None, :].expand(shape)
+        return row.to(dta), (-row).to(dtb), None
+
+
 def centroid_alignment_loss(img_embeds, txt_embeds, p=2):
-    """|| mean(img) - mean(txt) ||_p -- sparsify_clip.py:487-505 (O(B*D), unused by the YAMLs)."""
+    """|| mean(img) - mean(txt) ||_p -- sparsify_clip.py:487-505 (unused by the YAMLs).  CUDA tensors run on the
+    column-sum kernel; host tensors (the reference's own formula, for CPU-side checks) stay in PyTorch."""
+    if img_embeds.is_cuda and img_embeds.dim() == 2:
+        return _CentroidAlignFn.apply(img_embeds, txt_embeds, p)
     return torch.norm(img_embeds.mean(dim=0) - txt_embeds.mean(dim=0), p=p)

@@ -2,9 +2,9 @@
 (torch_uniformity1 :6, torch_uniformity :53, numpy_uniformity :101,
 torch_uniformity_equivalent :138, uniformity10 :182).
 
-Evaluation-only and cold: one D x B . B x D covariance (<= 0.1 % of a B x B x D contraction)
-plus a D x D eigen-decomposition, which is a cuSOLVER library call.  Kept as thin PyTorch
-functions; all five variants share one implementation of
+Evaluation-only and cold: one D x B . B x D covariance (<= 0.1 % of a B x B x D contraction; on CUDA tensors
+the library's scb_gram_dd kernel) plus a D x D eigen-decomposition, which is a cuSOLVER library call.
+All five variants share one implementation of
     W2 = sqrt(|mu|^2 + 1 + tr(Sigma) - (2/sqrt(D)) tr(Sigma^(1/2)))
 and differ only in the details the reference differs in (sign, epsilon, decomposition).
 """
@@ -14,7 +14,15 @@ import torch
 
 
 def _moments(x):
+    """(mean [1, D], covariance [D, D]); CUDA inputs run on the library's column-sum and D x D second-moment kernels
+    (scb_col_sum, scb_gram_dd: fp32 FMAs, fixed-order reductions), host inputs on the reference's own two lines."""
     n = x.size(0)
+    if x.is_cuda and x.dim() == 2:
+        from .backend_cuda import get_backend
+        be = get_backend()
+        xp = be.prep(x)
+        mu = be.col_sum(xp, None, 1.0 / n)
+        return mu[None, :], be.gram_dd(xp, mu, 1.0 / n)
     mu = x.mean(dim=0, keepdim=True)
     xc = x - mu
     return mu, torch.mm(xc.t(), xc) / n
@@ -44,6 +52,9 @@ def torch_uniformity(features_modality1, features_modality2):
 def numpy_uniformity(features_modality1, features_modality2):
     import numpy as np
     x = torch.cat([features_modality1, features_modality2], dim=0)
+    if x.is_cuda:                      # GPU-resident: eigenvalues only, no NumPy round trip (see metrics.uniformity)
+        from .metrics import uniformity as _gpu_uniformity
+        return _gpu_uniformity(features_modality1, features_modality2)
     mu, sigma = _moments(x)
     cov = sigma.detach().cpu().numpy()
     m = mu.detach().cpu().numpy().ravel()

@@ -98,3 +98,23 @@ def test_reference_eval_script_uniformity_matches_numpy_uniformity():
     ref, uni = _ref()
     I, T = _inputs(B=128, D=16)
     assert pu.numpy_uniformity(I, T) == pytest.approx(ref.uniformity(I, T), rel=1e-10)
+
+
+def test_eval_metric_restatements_match_the_reference(capsys):
+    """oracle/closed_form.py's restatements of the evaluation-side consumers (sparsify_clip.py:357-528) against the
+    unmodified reference: ranks and R@k (paired ids and a multi-caption id list), gap, mean angular value, true-pair
+    cosine, W2 uniformity."""
+    ref, _ = _ref()
+    I, T = _inputs(B=96, D=16, dtype=torch.float32)
+    S = T @ I.t()                                            # [N_text, N_image], as sparsify_clip.py:628
+    for ids, ids_txt in ((list(range(96)), list(range(96))),
+                         (list(range(48)), [k // 2 for k in range(96)])):      # two captions per image
+        Sx = S[:, :len(ids)]
+        fwd, bwd = cf.retrieval_ranks(Sx.numpy(), ids, ids_txt)
+        assert cf.recall_log(fwd, "forward") == ref.compute_metric_ret(Sx, ids, ids_txt, "forward")
+        assert cf.recall_log(bwd, "backward") == ref.compute_metric_ret(Sx, ids, ids_txt, "backward")
+    assert cf.compute_gap(I.numpy(), T.numpy()) == pytest.approx(ref.compute_gap(I, T), rel=1e-5)
+    assert cf.mean_angular_value(I.numpy()) == pytest.approx(ref.compute_mean_angular_value_of_a_modality(I), rel=1e-4, abs=1e-7)
+    assert cf.mean_true_pair_cosine(I.numpy(), T.numpy()) == pytest.approx(ref.mean_distance_of_true_pairs(I, T), rel=1e-5)
+    assert cf.w2_uniformity(I.numpy(), T.numpy()) == pytest.approx(ref.uniformity(I, T), rel=1e-5)
+    capsys.readouterr()
