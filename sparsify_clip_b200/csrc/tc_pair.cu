@@ -46,6 +46,7 @@ constexpr uint32_t kColOut = 0, kColS0 = 256;
 
 struct PairParams {
   int64_t nA, nB;
+  int64_t slot_rows;           // rows of one output partial slot (= nA unless this launch covers a row range of a larger pass)
   int D, kch, n_rb, n_jb, jparts, nslots, fmt;
   int64_t span;                // tiles of the linearised (row block, column tile) space per CTA pair
   float p0;
@@ -538,7 +539,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         ptx::mbar_wait(bar(BAR_OUT_FULL), item_cnt & 1u, 320);
         ptx::tc_fence_after();
         const int ncol_half = 32 * gch;  // columns of OUT handled by this warp
-        float* orow = P.out + ((int64_t)jp * P.nA + gi) * P.D;
+        float* orow = P.out + ((int64_t)jp * P.slot_rows + gi) * P.D;
         for (int c0 = 0; c0 < ncol_half; c0 += 32) {
           uint32_t v[32];
           const int ocol = h * ncol_half + c0;
@@ -563,7 +564,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) ptx::mbar_arrive(bar(BAR_OUT_EMPTY));
       }
       if (row_ok) {   // statistics over MY tiles only: 4 sub-partials per part (CTA rank x column half)
-        const int64_t o = ((int64_t)jp * 4 + 2 * (int)crank + h) * P.nA + gi;
+        const int64_t o = ((int64_t)jp * 4 + 2 * (int)crank + h) * P.slot_rows + gi;
         if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
         if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
       }
@@ -572,12 +573,12 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (row_ok && jb_lo + nt == P.n_jb) {
         const int ncol_half = 32 * gch;
         for (int sl = jp + 1; sl < P.jparts; ++sl) {
-          float* orow = P.out + ((int64_t)sl * P.nA + gi) * P.D + 256 * (int)crank + h * ncol_half;
+          float* orow = P.out + ((int64_t)sl * P.slot_rows + gi) * P.D + 256 * (int)crank + h * ncol_half;
           for (int c = 0; c < ncol_half; c += 4) {
             if (256 * (int)crank + h * ncol_half + c + 4 <= P.D) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
             else for (int cc2 = 0; cc2 < 4; ++cc2) if (256 * (int)crank + h * ncol_half + c + cc2 < P.D) orow[c + cc2] = 0.f;
           }
-          const int64_t o = ((int64_t)sl * 4 + 2 * (int)crank + h) * P.nA + gi;
+          const int64_t o = ((int64_t)sl * 4 + 2 * (int)crank + h) * P.slot_rows + gi;
           if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = 0.f;
           if (MODE == M_LUNIF_GRAD) { P.s0[o] = 0.f; P.s1[o] = 0.f; }
         }
@@ -692,9 +693,10 @@ namespace {
 
 template <int MODE>
 int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
-                PairParams P, cudaStream_t s) {
+                PairParams P, cudaStream_t s, int max_pairs = 0) {
   if (nA == 0) return 0;
   P.nA = nA; P.nB = nB; P.D = D;
+  if (P.slot_rows == 0) P.slot_rows = nA;
 #ifdef SCB_PAIR_TRACE
   P.trace = g_pair_trace.load();
 #endif
@@ -729,8 +731,8 @@ int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
     if (e != cudaSuccess) { scb_set_error("cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e)); return (int)e; }
   }
   int n_pairs = 1, pmax = 1;
-  scb_pair_span_plan(P.n_rb, P.n_jb, num_sms, &n_pairs, &P.span, &pmax);
-  SCB_CHECK_ARG(P.jparts == pmax, SCB_E_ARG, "pair kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
+  scb_pair_span_plan(P.n_rb, P.n_jb, max_pairs > 0 ? 2 * max_pairs : num_sms, &n_pairs, &P.span, &pmax);
+  SCB_CHECK_ARG(P.jparts >= pmax, SCB_E_ARG, "pair kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
                 P.jparts, pmax);
   if (P.kch == 8) k_tc_pair<MODE, 8><<<2 * n_pairs, kThreads, smem, s>>>(tmA, tmB, P);
   else k_tc_pair<MODE, 0><<<2 * n_pairs, kThreads, smem, s>>>(tmA, tmB, P);
@@ -755,6 +757,18 @@ int scb_tc_pair_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll
   P.jparts = jparts; P.p0 = t * SCB_LOG2E; P.rowvec = sqn_r; P.colvec = sqn_all; P.diag_off = row_offset;
   P.out = U; P.s0 = rq; P.s1 = rs;
   return launch_pair<M_LUNIF_GRAD>(Xr, nR, Xall, nAll, D, ldR, ldAll, dtype, P, s);
+}
+
+// A row range of a larger pass on at most `max_pairs` CTA pairs (tc_quad.cu runs it on the SMs that clusters of 4
+// cannot use): `row_base` rows precede A's first row in the pass, `slot_rows` = rows of the whole pass.
+int scb_tc_pair_range(int mode, const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                      float p0, const float* rowvec, const float* colvec, int64_t diag_off, int jparts, int64_t slot_rows,
+                      float* out, float* s0, float* s1, int max_pairs, cudaStream_t s) {
+  PairParams P{};
+  P.jparts = jparts; P.p0 = p0; P.rowvec = rowvec; P.colvec = colvec; P.diag_off = diag_off; P.slot_rows = slot_rows;
+  P.out = out; P.s0 = s0; P.s1 = s1;
+  return mode == M_ANCHOR_GRAD ? launch_pair<M_ANCHOR_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s, max_pairs)
+                               : launch_pair<M_LUNIF_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s, max_pairs);
 }
 
 unsigned long long* scb_pair_trace_buffer() {

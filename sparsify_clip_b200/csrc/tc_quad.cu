@@ -57,6 +57,7 @@ constexpr uint32_t kColOut = 0, kColS0 = 256;
 
 struct QuadParams {
   int64_t nA, nB;
+  int64_t slot_rows;           // rows of one output partial slot (= rows of the whole pass; this launch may cover a row range)
   int D, kch, n_rp, n_jb, jparts, nslots, fmt;
   int64_t span;                // tiles of the linearised (256-row block, column tile) space per cluster
   float p0;
@@ -638,7 +639,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (nt > 0) {
         ptx::mbar_wait(bar(BAR_OUT_FULL), item_cnt & 1u, 320);
         ptx::tc_fence_after();
-        float* orow = P.out + ((int64_t)jp * P.nA + gi) * P.D;
+        float* orow = P.out + ((int64_t)jp * P.slot_rows + gi) * P.D;
         for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t v[32];
           const int ocol = hh * 128 + c0;
@@ -663,7 +664,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) mbar_arrive_cluster(l_out_empty);
       }
       if (row_ok) {   // statistics over MY pair's tiles only: 4 sub-partials per part (pair x column half)
-        const int64_t o = ((int64_t)jp * 4 + 2 * (int)h + hh) * P.nA + gi;
+        const int64_t o = ((int64_t)jp * 4 + 2 * (int)h + hh) * P.slot_rows + gi;
         if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
         if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
       }
@@ -672,12 +673,12 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (row_ok && jb_lo + nt == P.n_jb) {
         for (int sl = jp + 1; sl < P.jparts; ++sl) {
           const int dbase = 256 * (int)h + hh * 128;
-          float* orow = P.out + ((int64_t)sl * P.nA + gi) * P.D + dbase;
+          float* orow = P.out + ((int64_t)sl * P.slot_rows + gi) * P.D + dbase;
           for (int cx = 0; cx < 128; cx += 4) {
             if (dbase + cx + 4 <= P.D) *reinterpret_cast<float4*>(orow + cx) = make_float4(0.f, 0.f, 0.f, 0.f);
             else for (int c2 = 0; c2 < 4; ++c2) if (dbase + cx + c2 < P.D) orow[cx + c2] = 0.f;
           }
-          const int64_t o = ((int64_t)sl * 4 + 2 * (int)h + hh) * P.nA + gi;
+          const int64_t o = ((int64_t)sl * 4 + 2 * (int)h + hh) * P.slot_rows + gi;
           if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = 0.f;
           if (MODE == M_LUNIF_GRAD) { P.s0[o] = 0.f; P.s1[o] = 0.f; }
         }
@@ -747,6 +748,10 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 }  // namespace
+
+int scb_tc_pair_range(int mode, const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                      float p0, const float* rowvec, const float* colvec, int64_t diag_off, int jparts, int64_t slot_rows,
+                      float* out, float* s0, float* s1, int max_pairs, cudaStream_t s);
 
 unsigned long long* scb_pair_trace_buffer();   // tc_pair.cu (null unless built with -DSCB_PAIR_TRACE and armed)
 int scb_make_tmap_2d_box(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype, int box_rows);   // tc_pass.cu
@@ -819,13 +824,87 @@ int scb_quad_clusters() {
   return n > 0 ? n : 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Hybrid split.  Clusters of 4 cannot use every SM (GPCs of 18 SMs strand one TPC each: 33 clusters = 132 of a B200's
+// 148 SMs), so a pass is cut by ROWS: the clusters of 4 take the first rows, and the CTA-pair kernel (tc_pair.cu) takes
+// the last rows on the stranded TPCs, concurrently.  The quad kernel is launched on an internal HIGH-PRIORITY stream so
+// that the block scheduler places its clusters first; the pair kernel follows on the caller's stream and fills what is
+// left.  Both write the same partial-slot layout ([jparts][rows of the pass][D], slot_rows); both zero the slots they
+// do not use, so `jparts` is simply the larger of the two plans.
+#ifndef SCB_QUAD_SIDE_PERMILLE
+#define SCB_QUAD_SIDE_PERMILLE 75      // share of the rows given to the stranded SMs (8 pairs at ~0.8 x the per-SM rate)
+#endif
+struct QuadSplit {
+  int64_t rows_quad;      // rows [0, rows_quad) -> clusters of 4 ; the rest -> CTA pairs
+  int side_pairs;         // CTA pairs that fit next to the clusters (0 = no split)
+  int jparts;
+};
+int scb_tc_flags_get();
+QuadSplit scb_quad_split(int64_t nA, int64_t nB, int n_sm) {
+  QuadSplit q{nA, 0, 1};
+  const int n_cl = scb_quad_clusters();
+  const int64_t n_jb = (nB + 127) / 128;
+  const int side = n_cl > 0 ? (n_sm - 4 * n_cl) / 2 : 0;
+  const int64_t n_rb = (nA + 127) / 128;
+  if ((scb_tc_flags_get() & 8) && side >= 2 && n_rb >= 64) {
+    int64_t rb_side = (n_rb * SCB_QUAD_SIDE_PERMILLE + 500) / 1000;
+    rb_side &= ~(int64_t)1;                                   // the clusters keep whole 256-row blocks
+    if (rb_side >= 2 && rb_side < n_rb - 2) {
+      q.rows_quad = (n_rb - rb_side) * 128;
+      q.side_pairs = side;
+    }
+  }
+  int nc = 0, pm = 1;
+  int64_t span = 0;
+  scb_quad_span_plan((q.rows_quad + 255) / 256, n_jb, n_cl > 0 ? n_cl : 1, &nc, &span, &pm);
+  q.jparts = pm;
+  if (q.side_pairs) {
+    void scb_pair_span_plan(int64_t, int64_t, int, int*, int64_t*, int*);
+    int np = 0, pp = 1;
+    scb_pair_span_plan((nA - q.rows_quad + 127) / 128, n_jb, 2 * q.side_pairs, &np, &span, &pp);
+    if (pp > q.jparts) q.jparts = pp;
+  }
+  return q;
+}
+
 namespace {
 
+struct QuadSide {
+  cudaStream_t hi = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+std::atomic<QuadSide*> g_side[kScbMaxDevices];
+
+QuadSide* quad_side() {
+  const int dev = scb_current_device();
+  if (dev < 0 || dev >= kScbMaxDevices) return nullptr;
+  QuadSide* q = g_side[dev].load(std::memory_order_acquire);
+  if (q) return q;
+  QuadSide* n = new QuadSide();
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  if (cudaStreamCreateWithPriority(&n->hi, cudaStreamNonBlocking, hi) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->join, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    delete n;
+    return nullptr;
+  }
+  QuadSide* expect = nullptr;
+  if (!g_side[dev].compare_exchange_strong(expect, n, std::memory_order_acq_rel)) {   // another thread won: keep its
+    cudaStreamDestroy(n->hi); cudaEventDestroy(n->fork); cudaEventDestroy(n->join);
+    delete n;
+    return expect;
+  }
+  return n;
+}
+
 template <int MODE>
-int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
-                QuadParams P, cudaStream_t s) {
+int launch_quad_rows(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                     QuadParams P, cudaStream_t s) {
   if (nA == 0) return 0;
   P.nA = nA; P.nB = nB; P.D = D;
+  if (P.slot_rows == 0) P.slot_rows = nA;
   P.trace = scb_pair_trace_buffer();
   P.kch = (D + 63) / 64;
   P.n_rp = (int)((nA + 255) / 256);
@@ -853,11 +932,42 @@ int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
   SCB_CHECK_ARG(n_cl > 0, SCB_E_SHAPE, "this device cannot run clusters of 4 CTAs with 227 KB of shared memory");
   int n_used = 1, pmax = 1;
   scb_quad_span_plan(P.n_rp, P.n_jb, n_cl, &n_used, &P.span, &pmax);
-  SCB_CHECK_ARG(P.jparts == pmax, SCB_E_ARG, "quad kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
+  SCB_CHECK_ARG(P.jparts >= pmax, SCB_E_ARG, "quad kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
                 P.jparts, pmax);
   if (P.kch == 8) k_tc_quad<MODE, 8><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
   else k_tc_quad<MODE, 0><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
   SCB_CHECK_LAUNCH("tc_quad");
+  return 0;
+}
+
+template <int MODE>
+int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
+                QuadParams P, cudaStream_t s) {
+  if (nA == 0) return 0;
+  const QuadSplit q = scb_quad_split(nA, nB, scb_num_sms());
+  QuadSide* side = q.side_pairs ? quad_side() : nullptr;
+  P.slot_rows = nA;
+  if (!side) {
+    SCB_CHECK_ARG(q.side_pairs == 0, SCB_E_DRIVER, "quad kernel: could not create the internal stream of the row split");
+    return launch_quad_rows<MODE>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
+  }
+  // clusters of 4: rows [0, rows_quad) on the high-priority stream; CTA pairs: the remaining rows on the caller's stream
+  cudaError_t e = cudaEventRecord(side->fork, s);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(side->hi, side->fork, 0);
+  if (e != cudaSuccess) { scb_set_error("quad split (fork): %s", cudaGetErrorString(e)); return (int)e; }
+  int rc = launch_quad_rows<MODE>(A, q.rows_quad, Bm, nB, D, ldA, ldB, dtype, P, side->hi);
+  const int64_t r0 = q.rows_quad;
+  const char* A2 = static_cast<const char*>(A) + (size_t)r0 * (size_t)ldA * 2u;
+  int rc2 = 0;
+  if (rc == 0)
+    rc2 = scb_tc_pair_range(MODE, A2, nA - r0, Bm, nB, D, ldA, ldB, dtype, P.p0, P.rowvec + r0, P.colvec, P.diag_off + r0, P.jparts, nA,
+                            P.out + (size_t)r0 * D, P.s0 ? P.s0 + r0 : nullptr, P.s1 ? P.s1 + r0 : nullptr, q.side_pairs, s);
+  // always join, also after a failed launch: the caller's stream must not be left without the dependency
+  e = cudaEventRecord(side->join, side->hi);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(s, side->join, 0);
+  if (rc) return rc;
+  if (rc2) return rc2;
+  if (e != cudaSuccess) { scb_set_error("quad split (join): %s", cudaGetErrorString(e)); return (int)e; }
   return 0;
 }
 

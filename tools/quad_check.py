@@ -36,14 +36,15 @@ import ctypes
 u = ctypes.c_int(0)
 be.lib.scb_set_tc_flags(7)
 print("grad kernel kind at nA=384, D=512:", be.lib.scb_grad_kernel_kind(384, 512, 148, ctypes.byref(u)), "units", u.value, flush=True)
+QF = int(os.environ.get("QUAD_FLAGS", "15"))
 ok = True
 sizes = [(256, 512, 0.1), (384, 512, 0.1), (129, 264, 0.1), (640, 320, 0.1), (385, 384, 0.07), (1300, 448, 0.1), (2100, 456, 0.05),
-         (1024, 512, 0.1), (5000, 512, 0.1)]
+         (1024, 512, 0.1), (5000, 512, 0.1), (8192, 512, 0.1), (12000, 448, 0.1)]
 if len(sys.argv) > 1 and sys.argv[1] == "first":
     sizes = sizes[:2]
 for (B, D, tau) in sizes:
     t0 = time.time()
-    Iq, Tq, l7, dI7, dT7, dt7 = run(B, D, tau, 7)
+    Iq, Tq, l7, dI7, dT7, dt7 = run(B, D, tau, QF)
     _, _, l3, dI3, dT3, dt3 = run(B, D, tau, 3)
     ref, dI, dT, dtau, _ = cf.weighted_loss(Iq.cpu().numpy(), Tq.cpu().numpy(), tau, 1.0, 1.0, 0.5, 0.5, 0.0)
     e_pair = max(np.linalg.norm(dI7 - dI3) / np.linalg.norm(dI3), np.linalg.norm(dT7 - dT3) / np.linalg.norm(dT3))
@@ -62,7 +63,7 @@ for (nA, nB, D) in [(32768, 32768, 512), (4096, 32768, 512)]:
     g = torch.Generator(device="cuda").manual_seed(1)
     X = torch.nn.functional.normalize(torch.randn(nB, D, generator=g, device="cuda"), dim=-1).to(torch.bfloat16)
     Xr = X[:nA]
-    for flags in (3, 7):
+    for flags in (3, 7, 15):
         be.lib.scb_set_tc_flags(flags)
         for _ in range(3):
             be.lunif_core(Xr, X, 2.0, 0, True)
