@@ -159,6 +159,14 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t a, ui
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// idle time between two remote stores of a sender thread (see kSendPaceClk)
+__device__ __forceinline__ void send_pace() {
+#ifdef SCB_QUAD_PACE_SLEEP
+  if (kSendPaceClk) __nanosleep((unsigned)(kSendPaceClk * 10 / 17));       // cycles -> ns at ~1.7 GHz; no issue slots burnt
+#else
+  if (kSendPaceClk) { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
+#endif
+}
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 // waits on barriers that CTAs other than the waiter's complete: acquire at cluster scope
@@ -720,13 +728,13 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int u = 0; u < 8; ++u) {
           st_async_v4(row_addr + (uint32_t)((u ^ (rrow & 7)) << 4), w0[4 * u], w0[4 * u + 1], w0[4 * u + 2], w0[4 * u + 3],
                       peer_w_full);
-          if (kSendPaceClk) { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
+          send_pace();
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           st_async_v4(row_addr + kSlotBytes + (uint32_t)((u ^ (rrow & 7)) << 4), w1[4 * u], w1[4 * u + 1], w1[4 * u + 2],
                       w1[4 * u + 3], peer_w_full);
-          if (kSendPaceClk) { const long long c0 = clock64(); while (clock64() - c0 < kSendPaceClk) {} }
+          send_pace();
         }
         if (lane == 0) tr.rec(52, kx);
       }
@@ -832,7 +840,7 @@ int scb_quad_clusters() {
 // left.  Both write the same partial-slot layout ([jparts][rows of the pass][D], slot_rows); both zero the slots they
 // do not use, so `jparts` is simply the larger of the two plans.
 #ifndef SCB_QUAD_SIDE_PERMILLE
-#define SCB_QUAD_SIDE_PERMILLE 75      // share of the rows given to the stranded SMs (8 pairs at ~0.8 x the per-SM rate)
+#define SCB_QUAD_SIDE_PERMILLE 60      // share of the rows given to the stranded SMs (8 pairs at ~0.8 x the per-SM rate)
 #endif
 struct QuadSplit {
   int64_t rows_quad;      // rows [0, rows_quad) -> clusters of 4 ; the rest -> CTA pairs
