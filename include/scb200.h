@@ -242,6 +242,21 @@ int scb_rank_count(const void* S, int64_t n_lines, int64_t n_elem, int64_t strid
 int scb_rank_count_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                         const float* gt_score, int64_t diag_off, int jparts, float* cnt, int path, void* stream);
 
+/* ------------------------------------------------------------------ SM-free all-gather inside one node
+ * Every rank pushes its row shard into every peer's gather buffer with the copy engines and then writes an epoch flag;
+ * the consumer waits on its own flags with a one-warp kernel.  The buffers are the one thing the library allocates
+ * (explicit alloc / open / close, like a communicator handle): scb_peer_alloc -> device memory + a 64-byte CUDA IPC
+ * handle to hand to the other processes; scb_peer_open maps a peer's buffer (peer access enabled lazily);
+ * scb_peer_close(ptr, opened) unmaps (opened = 1) or frees (opened = 0). */
+int scb_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
+int scb_peer_open(const unsigned char* handle64, void** ptr);
+int scb_peer_close(void* ptr, int opened);
+/* stream-ordered: bytes from src to each dst[k], then the int at epoch_src to each flag[k] (k < n) */
+int scb_peer_push(const void* src, int64_t bytes, void* const* dst, void* const* flag, int n, const int* epoch_src,
+                  void* stream);
+/* stream-ordered wait until flags[i] >= epoch for every i < n (n <= 32) */
+int scb_wait_flags(const int* flags, int n, int epoch, void* stream);
+
 /* debug: device buffer of 2 x 4 x 4096 x 2 uint64 that the CTA-pair kernel fills with a per-role timeline of
  * cluster 0 (tag, tile, clock64) on the following launches; NULL switches it off (tools/pair_trace.py). */
 int scb_debug_pair_trace(void* buf);

@@ -55,6 +55,11 @@ SIGNATURES = {
     "scb_rows_times_dd": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp],
     "scb_sum_parts": [_vp, _i32, _i64, _f32, _vp, _vp],
     "scb_rank_count": [_vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _vp],
+    "scb_peer_alloc": [_i64, ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p],
+    "scb_peer_open": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)],
+    "scb_peer_close": [_vp, _i32],
+    "scb_peer_push": [_vp, _i64, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _i32, _vp, _vp],
+    "scb_wait_flags": [_vp, _i32, _i32, _vp],
     "scb_rank_count_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _vp],
 }
 

@@ -8,6 +8,8 @@
 //   * rank of the ground-truth entry of every row / column of a given score matrix -> compute_metric_ret (:357-416)
 // All fp32 on CUDA cores with fixed-order two-stage reductions (bit-reproducible); none of them is on the training
 // step's critical path (2 B D^2 is <= 0.1 % of one B x B x D contraction).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -226,5 +228,78 @@ extern "C" int scb_rank_count(const void* S, int64_t n_lines, int64_t n_elem, in
   k_rank_count<<<(unsigned)((n_lines + 7) / 8), 256, 0, (cudaStream_t)stream>>>(S, n_lines, n_elem, stride_line, stride_elem,
                                                                              dtype, line, gt, rank);
   SCB_CHECK_LAUNCH("rank_count");
+  return 0;
+}
+
+// ===================================================================================================================
+// SM-free row all-gather between the GPUs of one node.  NCCL's all-gather is a kernel: it takes
+// SMs away from the persistent sweeps it is meant to overlap with (measured at 8 GPUs: a sweep that shares the machine
+// with ncclDevKernel_AllGather_RING_LL runs 270 us instead of 217 us).  Here every rank PUSHES its shard into every peer's
+// gather buffer with the copy engines (cudaMemcpyAsync on peer-mapped pointers over NVLink), followed by a 4-byte
+// "epoch" flag per peer on the same stream; the only kernel is the consumer's one-warp wait on its own flag words.
+// Buffers are exchanged once through CUDA IPC (explicit alloc / open / close: the one place where the library owns
+// device memory, as the communicator-handle exception of the boundary contract allows).
+// ===================================================================================================================
+namespace {
+__global__ void k_wait_flags(const volatile int* __restrict__ flags, int n, int epoch) {
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  long long t0 = 0;
+  bool timed = false;
+  while (flags[i] < epoch) {
+    if (!timed) { t0 = (long long)clock64(); timed = true; }
+    // ~30 s at 2 GHz: a peer that never arrives must end the job, not hang the GPU
+    if ((long long)clock64() - t0 > 60000000000ll) __trap();
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+}  // namespace
+
+extern "C" int scb_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64) {
+  SCB_CHECK_ARG(bytes > 0 && ptr && handle64, SCB_E_ARG, "peer_alloc: bad argument");
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(*ptr, 0, (size_t)bytes);
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) { scb_set_error("peer_alloc: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+extern "C" int scb_peer_open(const unsigned char* handle64, void** ptr) {
+  SCB_CHECK_ARG(handle64 && ptr, SCB_E_ARG, "peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { scb_set_error("peer_open: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+  return 0;
+}
+extern "C" int scb_peer_close(void* ptr, int opened) {
+  const cudaError_t e = opened ? cudaIpcCloseMemHandle(ptr) : cudaFree(ptr);
+  if (e != cudaSuccess) { scb_set_error("peer_close: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
+  return 0;
+}
+// copy `bytes` from src to each dst[k] (peer-mapped or local), then the 4 bytes at epoch_src to each flag[k]: all on
+// `stream`, in this order, so a flag can only be seen after the shard it announces has landed
+extern "C" int scb_peer_push(const void* src, int64_t bytes, void* const* dst, void* const* flag, int n, const int* epoch_src,
+                             void* stream) {
+  SCB_CHECK_ARG(src && dst && flag && epoch_src && n >= 0 && bytes >= 0, SCB_E_ARG, "peer_push: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int k = 0; k < n; ++k) {
+    const cudaError_t e = cudaMemcpyAsync(dst[k], src, (size_t)bytes, cudaMemcpyDefault, s);
+    if (e != cudaSuccess) { scb_set_error("peer_push (data %d): %s", k, cudaGetErrorString(e)); return (int)e; }
+  }
+  for (int k = 0; k < n; ++k) {
+    const cudaError_t e = cudaMemcpyAsync(flag[k], epoch_src, 4, cudaMemcpyDefault, s);
+    if (e != cudaSuccess) { scb_set_error("peer_push (flag %d): %s", k, cudaGetErrorString(e)); return (int)e; }
+  }
+  return 0;
+}
+// stream-ordered wait until flags[i] >= epoch for all i < n (n <= 32): one warp, no other SM use
+extern "C" int scb_wait_flags(const int* flags, int n, int epoch, void* stream) {
+  SCB_CHECK_ARG(flags && n >= 1 && n <= 32, SCB_E_ARG, "wait_flags: bad argument");
+  k_wait_flags<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n, epoch);
+  SCB_CHECK_LAUNCH("wait_flags");
   return 0;
 }

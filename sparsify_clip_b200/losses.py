@@ -50,12 +50,39 @@ def _all_gather_rows(x, group):
     return out
 
 
-def _all_gather_rows_async(x, group):
-    """-> (gathered tensor, work handle); the caller waits on the handle before the first use."""
+def _all_gather_rows_async(x, group, role=None):
+    """-> (gathered tensor, work handle); the caller waits on the handle before the first use.  With a `role` the gather
+    goes through the SM-free peer pushes of peer.py when the ranks share a node (the result then lives in a per-role
+    double buffer: valid until the second next gather of the same role); otherwise through NCCL."""
+    if role is not None:
+        from . import peer
+        got = peer.all_gather_async(x, group, role)
+        if got is not None:
+            return got
     ws = dist.get_world_size(group)
     x = x.contiguous()
     out = torch.empty((ws * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     return out, dist.all_gather_into_tensor(out, x, group=group, async_op=True)
+
+
+class _SmallReduce:
+    """Asynchronous sum over the ranks of a few floats: gathered with the SM-free peer pushes (role-keyed double buffer) and
+    added locally when the ranks share a node -- no NCCL kernel sits on the SMs while the sweeps run -- else NCCL."""
+
+    def __init__(self, x, group, role):
+        self.x, self.h, self.gathered = x, None, None
+        got = None
+        if x.is_cuda:
+            from . import peer
+            got = peer.all_gather_async(x.contiguous().view(1, -1), group, role)
+        if got is not None:
+            self.gathered, self.h = got
+        else:
+            self.h = dist.all_reduce(x, group=group, async_op=True)
+
+    def result(self):
+        self.h.wait()
+        return self.x if self.gathered is None else self.gathered.sum(0)
 
 
 def _all_reduce_(x, group):
@@ -247,11 +274,11 @@ class _FusedTermsFn(torch.autograd.Function):
             C_all = Cq
         if group is not None:
             if w_a != 0.0 or w_i != 0.0:
-                I_all, hI = _all_gather_rows_async(Ip, group)
+                I_all, hI = _all_gather_rows_async(Ip, group, "I")
             if w_a != 0.0 or w_t != 0.0:
-                T_all, hT = _all_gather_rows_async(Tp, group)
+                T_all, hT = _all_gather_rows_async(Tp, group, "T")
             if w_c != 0.0:
-                C_all, hC = _all_gather_rows_async(Cq, group)
+                C_all, hC = _all_gather_rows_async(Cq, group, "C")
 
         def _await(h):
             if h is not None:
@@ -309,8 +336,7 @@ class _FusedTermsFn(torch.autograd.Function):
                 _, cM, cL, c_exact, flag = colparts
                 pieces = (r, c_exact, parts[:NP], cM, cL)
             pack = torch.cat([x.to(torch.float32) for x in pieces])
-            pack_flat = torch.empty(ws * pack.numel(), dtype=torch.float32, device=dev)
-            hP = dist.all_gather_into_tensor(pack_flat, pack, group=group, async_op=True)
+            pack_flat, hP = _all_gather_rows_async(pack, group, "P")
             gathered = True
         hT = _await(hT)
         _unif(w_t, Tp, T_all, need_T, "T", 5)
@@ -339,25 +365,21 @@ class _FusedTermsFn(torch.autograd.Function):
         if w_a != 0.0 and (need or need_tau):
             coef = w_a * scale / (2.0 * B)
             if group is not None and (not gathered or w_t != 0.0 or w_c != 0.0):
-                late = parts[late_lo:NS].clone()             # reduced under the anchor-gradient sweeps
-                hR = dist.all_reduce(late, group=group, async_op=True)
+                hR = _SmallReduce(parts[late_lo:NS].clone(), group, "R")      # reduced under the anchor-gradient sweeps
             if need_I or need_tau:
                 p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
                 an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef)
                 if need_tau:
                     parts[NS] = p["ws"] - 2.0 * local_sdiag
                     if group is not None:                    # reduced under the dT sweep
-                        dtau_part = parts[NS:].clone()
-                        hD = dist.all_reduce(dtau_part, group=group, async_op=True)
+                        hD = _SmallReduce(parts[NS:].clone(), group, "D")
             if need_T:
                 p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
                 an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
             if hR is not None:
-                hR = _await(hR)
-                parts[late_lo:NS] = late
+                parts[late_lo:NS] = hR.result()
             if hD is not None:
-                hD = _await(hD)
-                parts[NS:] = dtau_part
+                parts[NS:] = hD.result()
         # the additions of the ladder on the (now global) partial sums, and 1 / Ssum of every L_unif term, in one launch
         loss, inv_ssum = be.loss_assemble(parts, w_a / (2.0 * B), 2.0 * scale, w_l / B, w_i, w_t, w_c, B * (B - 1) / 2.0)
         cen = un_I = un_T = None
