@@ -251,11 +251,18 @@ int scb_rank_count_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, i
 int scb_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64);
 int scb_peer_open(const unsigned char* handle64, void** ptr);
 int scb_peer_close(void* ptr, int opened);
-/* stream-ordered: bytes from src to each dst[k], then the int at epoch_src to each flag[k] (k < n) */
-int scb_peer_push(const void* src, int64_t bytes, void* const* dst, void* const* flag, int n, const int* epoch_src,
-                  void* stream);
-/* stream-ordered wait until flags[i] >= epoch for every i < n (n <= 32) */
-int scb_wait_flags(const int* flags, int n, int epoch, void* stream);
+/* One gather epoch of one role.  State per rank: a device int `epoch`, and in the IPC-shared buffer two int arrays
+ * arrived[world], done[world].  All calls are stream-ordered and read the epoch on the device (graph-replayable).
+ * scb_peer_begin (consumer's stream): ++epoch; wait until every peer released the previous epoch (done[p] >= epoch - 1).
+ * scb_peer_push (any stream ordered after begin): copy `bytes` from src to each dst[k] (k < n, copy engines), then store
+ *   epoch into *arrived_words[p] for every p < world (arrived_words / done_words: DEVICE arrays of `world` peer-mapped
+ *   pointers to this rank's word on each rank).
+ * scb_peer_wait: until arrived[p] >= epoch for every p.   scb_peer_release: store epoch into *done_words[p]. */
+int scb_peer_begin(int* epoch, const int* done, int world, void* stream);
+int scb_peer_push(const void* src, int64_t bytes, void* const* dst, int n, const int* epoch, int* const* arrived_words,
+                  int world, void* stream);
+int scb_peer_wait(const int* epoch, const int* arrived, int world, void* stream);
+int scb_peer_release(const int* epoch, int* const* done_words, int world, void* stream);
 
 /* debug: device buffer of 2 x 4 x 4096 x 2 uint64 that the CTA-pair kernel fills with a per-role timeline of
  * cluster 0 (tag, tile, clock64) on the following launches; NULL switches it off (tools/pair_trace.py). */

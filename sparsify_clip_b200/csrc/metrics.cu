@@ -241,17 +241,35 @@ extern "C" int scb_rank_count(const void* S, int64_t n_lines, int64_t n_elem, in
 // device memory, as the communicator-handle exception of the boundary contract allows).
 // ===================================================================================================================
 namespace {
-__global__ void k_wait_flags(const volatile int* __restrict__ flags, int n, int epoch) {
-  const int i = threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ void spin_until_ge(const volatile int* w, int v) {
   long long t0 = 0;
   bool timed = false;
-  while (flags[i] < epoch) {
+  while (*w < v) {
     if (!timed) { t0 = (long long)clock64(); timed = true; }
-    // ~30 s at 2 GHz: a peer that never arrives must end the job, not hang the GPU
-    if ((long long)clock64() - t0 > 60000000000ll) __trap();
-    __nanosleep(200);
+    if ((long long)clock64() - t0 > 60000000000ll) __trap();   // ~30 s: a peer that never arrives must end the job, not hang
+    __nanosleep(100);
   }
+}
+// All four protocol kernels are ONE warp (lane = peer index) and read the epoch from a device counter, so a step that
+// contains them can be replayed from a CUDA graph: nothing about the epoch is baked into the launch.
+//   begin:   ++epoch; wait until every peer has RELEASED the previous contents of its gather buffer (done[p] >= epoch-1)
+//   arrive:  (after the copy-engine pushes, same stream) arrived-word of every peer for my slot = epoch
+//   wait:    until every peer's shard of this epoch has arrived in MY buffer
+//   release: (after my last read) done-word of every peer for my slot = epoch
+__global__ void k_peer_begin(int* __restrict__ epoch, const volatile int* __restrict__ done, int world) {
+  int e = 0;
+  if (threadIdx.x == 0) { e = *epoch + 1; *epoch = e; }
+  e = __shfl_sync(0xffffffffu, e, 0);
+  if ((int)threadIdx.x < world) spin_until_ge(done + threadIdx.x, e - 1);
+}
+__global__ void k_peer_signal(const int* __restrict__ epoch, int* const* __restrict__ words, int world) {
+  if ((int)threadIdx.x < world) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(words[threadIdx.x]) = *epoch;
+  }
+}
+__global__ void k_peer_wait(const int* __restrict__ epoch, const volatile int* __restrict__ arrived, int world) {
+  if ((int)threadIdx.x < world) spin_until_ge(arrived + threadIdx.x, *epoch);
   __threadfence_system();
 }
 }  // namespace
@@ -280,26 +298,43 @@ extern "C" int scb_peer_close(void* ptr, int opened) {
   if (e != cudaSuccess) { scb_set_error("peer_close: %s", cudaGetErrorString(e)); cudaGetLastError(); return (int)e; }
   return 0;
 }
-// copy `bytes` from src to each dst[k] (peer-mapped or local), then the 4 bytes at epoch_src to each flag[k]: all on
-// `stream`, in this order, so a flag can only be seen after the shard it announces has landed
-extern "C" int scb_peer_push(const void* src, int64_t bytes, void* const* dst, void* const* flag, int n, const int* epoch_src,
-                             void* stream) {
-  SCB_CHECK_ARG(src && dst && flag && epoch_src && n >= 0 && bytes >= 0, SCB_E_ARG, "peer_push: bad argument");
+// One gather epoch, sender side.  scb_peer_begin goes on the CONSUMER's stream (it advances the epoch the later
+// scb_peer_wait on that stream compares against, and waits for the peers' release of the previous epoch);
+// scb_peer_push may go on a side stream that waits for it: `bytes` from src to each dst[k] with the copy engines
+// (peer-mapped or local pointers), then this rank's arrived-word on every peer.
+// epoch: device int owned by this role on this rank; done: my done[world] words; arrived_words: DEVICE array of `world`
+// pointers (peer-mapped) to arrived[my rank] on each rank.
+extern "C" int scb_peer_begin(int* epoch, const int* done, int world, void* stream) {
+  SCB_CHECK_ARG(epoch && done && world >= 1 && world <= 32, SCB_E_ARG, "peer_begin: bad argument");
+  k_peer_begin<<<1, 32, 0, (cudaStream_t)stream>>>(epoch, done, world);
+  SCB_CHECK_LAUNCH("peer_begin");
+  return 0;
+}
+extern "C" int scb_peer_push(const void* src, int64_t bytes, void* const* dst, int n, const int* epoch,
+                             int* const* arrived_words, int world, void* stream) {
+  SCB_CHECK_ARG(src && dst && epoch && arrived_words && n >= 0 && bytes >= 0 && world >= 1 && world <= 32, SCB_E_ARG,
+                "peer_push: bad argument");
   cudaStream_t s = (cudaStream_t)stream;
   for (int k = 0; k < n; ++k) {
     const cudaError_t e = cudaMemcpyAsync(dst[k], src, (size_t)bytes, cudaMemcpyDefault, s);
-    if (e != cudaSuccess) { scb_set_error("peer_push (data %d): %s", k, cudaGetErrorString(e)); return (int)e; }
+    if (e != cudaSuccess) { scb_set_error("peer_push (copy %d): %s", k, cudaGetErrorString(e)); return (int)e; }
   }
-  for (int k = 0; k < n; ++k) {
-    const cudaError_t e = cudaMemcpyAsync(flag[k], epoch_src, 4, cudaMemcpyDefault, s);
-    if (e != cudaSuccess) { scb_set_error("peer_push (flag %d): %s", k, cudaGetErrorString(e)); return (int)e; }
-  }
+  k_peer_signal<<<1, 32, 0, s>>>(epoch, arrived_words, world);
+  SCB_CHECK_LAUNCH("peer_push");
   return 0;
 }
-// stream-ordered wait until flags[i] >= epoch for all i < n (n <= 32): one warp, no other SM use
-extern "C" int scb_wait_flags(const int* flags, int n, int epoch, void* stream) {
-  SCB_CHECK_ARG(flags && n >= 1 && n <= 32, SCB_E_ARG, "wait_flags: bad argument");
-  k_wait_flags<<<1, 32, 0, (cudaStream_t)stream>>>(flags, n, epoch);
-  SCB_CHECK_LAUNCH("wait_flags");
+// receiver side: stream-ordered wait until every rank's shard of the current epoch has landed in my buffer
+extern "C" int scb_peer_wait(const int* epoch, const int* arrived, int world, void* stream) {
+  SCB_CHECK_ARG(epoch && arrived && world >= 1 && world <= 32, SCB_E_ARG, "peer_wait: bad argument");
+  k_peer_wait<<<1, 32, 0, (cudaStream_t)stream>>>(epoch, arrived, world);
+  SCB_CHECK_LAUNCH("peer_wait");
+  return 0;
+}
+// after the last read of my gather buffer: tell every peer it may overwrite its slot (done_words: device array of
+// `world` pointers to done[my rank] on each rank)
+extern "C" int scb_peer_release(const int* epoch, int* const* done_words, int world, void* stream) {
+  SCB_CHECK_ARG(epoch && done_words && world >= 1 && world <= 32, SCB_E_ARG, "peer_release: bad argument");
+  k_peer_signal<<<1, 32, 0, (cudaStream_t)stream>>>(epoch, done_words, world);
+  SCB_CHECK_LAUNCH("peer_release");
   return 0;
 }

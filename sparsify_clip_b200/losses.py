@@ -380,6 +380,9 @@ class _FusedTermsFn(torch.autograd.Function):
                 parts[late_lo:NS] = hR.result()
             if hD is not None:
                 parts[NS:] = hD.result()
+        if group is not None and Ip.is_cuda:
+            from . import peer
+            peer.release_all()          # every sweep that reads a gathered buffer is enqueued: the peers may refill them
         # the additions of the ladder on the (now global) partial sums, and 1 / Ssum of every L_unif term, in one launch
         loss, inv_ssum = be.loss_assemble(parts, w_a / (2.0 * B), 2.0 * scale, w_l / B, w_i, w_t, w_c, B * (B - 1) / 2.0)
         cen = un_I = un_T = None

@@ -1,18 +1,20 @@
-"""SM-free all-gather of row shards between the GPUs of one node (exchange step 1 and 2).
+"""SM-free all-gather of row shards between the GPUs of one node (exchange steps 1 and 2).
 
 NCCL's all-gather is a kernel: launched under a persistent sweep it takes SMs the sweep's clusters were sized for
 (measured at 8 GPUs: 270 us instead of 217 us per sweep) and, issued before one, it is fully exposed (~180 us for
 8 x 4 MB in the LL protocol).  Here every rank PUSHES its shard into every peer's gather buffer with the copy engines
-(`scb_peer_push`: cudaMemcpyAsync on peer-mapped pointers, NVLink), then writes a 4-byte epoch flag per peer on the same
-stream; the consumer's only kernel is a one-warp wait on its own flag words (`scb_wait_flags`).
+(`scb_peer_push`: cudaMemcpyAsync on peer-mapped pointers, NVLink); the only kernels are one-warp flag kernels.
 
-Buffers are allocated by the library (`scb_peer_alloc`) and exchanged once per (group, role, shard size) through CUDA
-IPC handles.  Each role ("I", "T", ...) owns TWO buffers used alternately: a rank can only be two gathers ahead of a peer
-after having seen that peer's flag of the gather in between, and a peer pushes only after everything it enqueued before
-(the sweeps that read the older buffer) has finished -- so the buffer being overwritten is no longer read anywhere.
+Protocol per role ("I", "T", "P", ...), one gather buffer per rank exchanged once through CUDA IPC:
+    begin    (consumer's stream)  ++epoch; wait until every peer RELEASED the previous contents of its buffer
+    push     (side stream)        my shard -> slot[rank] of every rank's buffer; then arrived[rank] := epoch on every rank
+    wait     (consumer's stream)  until arrived[p] >= epoch for every p: the gathered buffer is complete
+    release  (consumer's stream, after the last read)   done[rank] := epoch on every rank
+The epoch lives in device memory and every flag kernel reads it there, so a step that contains a gather can be captured
+into a CUDA graph and replayed (nothing about the epoch is baked into a launch).  A missing `release` (an exception
+between gather and release) makes the peers' next `begin` wait until the library's watchdog ends the job.
 
-Falls back to NCCL (the caller does) when the ranks are not all on one node, when CUDA IPC is unavailable, or while the
-stream is being captured into a CUDA graph (cross-device copies are not capturable).
+Falls back to NCCL (the caller does) when the ranks are not all on one node or CUDA IPC is unavailable.
 """
 import ctypes
 import os
@@ -24,8 +26,7 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import check
 
-_EPOCHS = 1 << 22          # table of epoch values on the device (16 MB): 4 M gathers per role before it is exhausted
-_state = {"mode": os.environ.get("SCB_GATHER", "auto"), "objs": {}, "ok": {}, "table": {}}
+_state = {"mode": os.environ.get("SCB_GATHER", "auto"), "objs": {}, "ok": {}, "open": []}
 
 
 def set_gather(mode):
@@ -44,73 +45,90 @@ class _Raw:
 
 
 class _Handle:
-    def __init__(self, pg, buf, epoch, keep):
-        self.pg, self.buf, self.epoch, self.keep = pg, buf, epoch, keep
+    def __init__(self, pg, keep):
+        self.pg, self.keep = pg, keep
 
     def wait(self):
         pg = self.pg
         st = torch.cuda.current_stream(pg.device).cuda_stream
-        check(pg.lib.scb_wait_flags(pg.base + pg.flag_off + 4 * self.buf * pg.world, pg.world, self.epoch, st), "wait_flags")
+        check(pg.lib.scb_peer_wait(pg.epoch.data_ptr(), pg.base + pg.arr_off, pg.world, st), "peer_wait")
         self.keep = None
 
 
 class PeerGather:
-    """One role's double-buffered gather area on every rank of `group` (all ranks on this node)."""
+    """One role's gather buffer on every rank of `group` (all ranks on this node)."""
 
     def __init__(self, group, shard_bytes, device):
         self.lib = _lib.load()
         self.group, self.device = group, device
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 32:
+            raise RuntimeError("peer gather supports up to 32 ranks")
         self.shard = int(shard_bytes)
         self.buf_bytes = ((self.shard * self.world + 255) // 256) * 256
-        self.flag_off = 2 * self.buf_bytes
-        total = self.flag_off + 4096
+        self.arr_off, self.done_off = self.buf_bytes, self.buf_bytes + 128
+        total = self.buf_bytes + 256
         ptr = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         with torch.cuda.device(device):
-            check(self.lib.scb_peer_alloc(total, ctypes.byref(ptr), handle), "peer_alloc")
+            check(self.lib.scb_peer_alloc(total, ctypes.byref(ptr), handle), "peer_alloc")     # zero-filled
         self.base = ptr.value
-        mine = (socket.gethostname(), device.index, handle.raw)
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=group)
-        if len({h for h, _, _ in everyone}) != 1:
+        dist.all_gather_object(everyone, (socket.gethostname(), handle.raw), group=group)
+        if len({h for h, _ in everyone}) != 1:
             raise RuntimeError("peer gather needs all ranks on one node")
         self.ptrs = []
         with torch.cuda.device(device):
-            for r, (_, _, hb) in enumerate(everyone):
+            for r, (_, hb) in enumerate(everyone):
                 if r == self.rank:
                     self.ptrs.append(self.base)
                 else:
                     p = ctypes.c_void_p()
                     check(self.lib.scb_peer_open(hb, ctypes.byref(p)), "peer_open")
                     self.ptrs.append(p.value)
-        self.view = torch.as_tensor(_Raw(self.base, 2 * self.buf_bytes), device=device)
+        self.view = torch.as_tensor(_Raw(self.base, self.buf_bytes), device=device)
         self.stream = torch.cuda.Stream(device=device)
-        key = device.index
-        if key not in _state["table"]:
-            _state["table"][key] = torch.arange(_EPOCHS, dtype=torch.int32, device=device)
-        self.table = _state["table"][key]
-        self.epoch = 0
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        i64 = dict(dtype=torch.int64, device=device)
+        self.arrived_words = torch.tensor([p + self.arr_off + 4 * self.rank for p in self.ptrs], **i64)
+        self.done_words = torch.tensor([p + self.done_off + 4 * self.rank for p in self.ptrs], **i64)
         order = [(self.rank + k) % self.world for k in range(1, self.world)] + [self.rank]     # peers first, then myself
-        VP = ctypes.c_void_p * self.world
-        self._dst = [VP(*[self.ptrs[p] + b * self.buf_bytes + self.rank * self.shard for p in order]) for b in (0, 1)]
-        self._flag = [VP(*[self.ptrs[p] + self.flag_off + 4 * (b * self.world + self.rank) for p in order]) for b in (0, 1)]
-        dist.barrier(group=group)              # everybody has mapped everybody before the first push
+        self._dst = (ctypes.c_void_p * self.world)(*[self.ptrs[p] + self.rank * self.shard for p in order])
+        self.open_reads = False
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)              # everybody has mapped everybody (and zeroed its flags) before the first push
 
     def gather(self, x):
-        """x: contiguous tensor of `shard` bytes on self.device.  -> (flat uint8 view of the gathered buffer, handle)."""
+        """x: contiguous tensor of `shard` bytes on self.device.  -> (flat uint8 view of the gather buffer, handle)."""
         assert x.is_contiguous() and x.numel() * x.element_size() == self.shard
-        self.epoch += 1
-        if self.epoch >= _EPOCHS:
-            raise RuntimeError("peer gather: epoch table exhausted")
-        b = self.epoch & 1
+        if self.open_reads:
+            raise RuntimeError("peer gather: the previous result of this role was never released (peer.release_all)")
         cur = torch.cuda.current_stream(self.device)
-        self.stream.wait_stream(cur)           # x, and every earlier read of the buffer about to be overwritten elsewhere
-        x.record_stream(self.stream)
-        check(self.lib.scb_peer_push(x.data_ptr(), self.shard, self._dst[b], self._flag[b], self.world,
-                                     self.table.data_ptr() + 4 * self.epoch, self.stream.cuda_stream), "peer_push")
-        out = self.view[b * self.buf_bytes:b * self.buf_bytes + self.shard * self.world]
-        return out, _Handle(self, b, self.epoch, x)
+        check(self.lib.scb_peer_begin(self.epoch.data_ptr(), self.base + self.done_off, self.world, cur.cuda_stream), "peer_begin")
+        self.stream.wait_stream(cur)           # x is ready, the epoch is advanced, the peers have released their buffers
+        # (x is kept alive by the handle until wait() is enqueued: the wait kernel only passes once my own pushes -- the
+        #  last thing to read x -- have set my arrived flag, and any reuse of x's memory is ordered after it on `cur`)
+        check(self.lib.scb_peer_push(x.data_ptr(), self.shard, self._dst, self.world, self.epoch.data_ptr(),
+                                     self.arrived_words.data_ptr(), self.world, self.stream.cuda_stream), "peer_push")
+        self.open_reads = True
+        if self not in _state["open"]:
+            _state["open"].append(self)
+        return self.view[:self.shard * self.world], _Handle(self, x)
+
+    def release(self):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.stream)           # joins the side stream (required inside a graph capture; cheap otherwise)
+        check(self.lib.scb_peer_release(self.epoch.data_ptr(), self.done_words.data_ptr(), self.world, cur.cuda_stream),
+              "peer_release")
+        self.open_reads = False
+
+
+def release_all():
+    """After the last read of every gathered buffer of this step (stream-ordered): let the peers overwrite them."""
+    for pg in _state["open"]:
+        if pg.open_reads:
+            pg.release()
+    _state["open"].clear()
 
 
 def available(group, device):
@@ -123,8 +141,10 @@ def available(group, device):
         try:
             if dist.get_backend(group) != "nccl" or not torch.cuda.is_available():
                 ok = 0
+            elif torch.cuda.is_current_stream_capturing():
+                ok = 0                                          # the one-time IPC exchange cannot happen inside a capture
             else:
-                PeerGather(group, 1024, device)                # probe: IPC exchange + mapping works on every rank
+                PeerGather(group, 1024, device)                 # probe: IPC exchange + mapping works on every rank
         except Exception:
             ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device=device if dist.get_backend(group) == "nccl" else "cpu")
@@ -137,14 +157,21 @@ def available(group, device):
 
 def all_gather_async(x, group, role):
     """All-gather the contiguous tensor x along dim 0 with peer pushes.  -> (gathered tensor, handle) or None when the
-    peer path does not apply (the caller then uses NCCL)."""
-    if not x.is_cuda or torch.cuda.is_current_stream_capturing() or not available(group, x.device):
+    peer path does not apply (the caller then uses NCCL).  The result lives in the role's buffer until release_all()."""
+    if not x.is_cuda:
+        return None
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing and (id(group), x.device.index) not in _state["ok"]:
+        return None
+    if not available(group, x.device):
         return None
     x = x.contiguous()
     nbytes = x.numel() * x.element_size()
     key = (id(group), x.device.index, role, nbytes)
     pg = _state["objs"].get(key)
     if pg is None:
+        if capturing:
+            return None                       # buffers must exist before a capture (run one eager step first)
         pg = _state["objs"][key] = PeerGather(group, nbytes, x.device)
     flat, h = pg.gather(x)
     out = flat.view(x.dtype).view((pg.world * x.shape[0],) + tuple(x.shape[1:]))
