@@ -261,6 +261,8 @@ int scb_peer_close(void* ptr, int opened);
 int scb_peer_begin(int* epoch, const int* done, int world, void* stream);
 int scb_peer_push(const void* src, int64_t bytes, void* const* dst, int n, const int* epoch, int* const* arrived_words,
                   int world, void* stream);
+/* the copies of scb_peer_push alone (several streams may share a large shard's pushes; scb_peer_push with n = 0 sends the flags) */
+int scb_peer_copy(const void* src, int64_t bytes, void* const* dst, int n, void* stream);
 int scb_peer_wait(const int* epoch, const int* arrived, int world, void* stream);
 int scb_peer_release(const int* epoch, int* const* done_words, int world, void* stream);
 

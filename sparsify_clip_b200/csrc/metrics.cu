@@ -323,6 +323,15 @@ extern "C" int scb_peer_push(const void* src, int64_t bytes, void* const* dst, i
   SCB_CHECK_LAUNCH("peer_push");
   return 0;
 }
+// the copies alone (to spread a large shard's pushes over several streams; scb_peer_push with n = 0 then sends the flag)
+extern "C" int scb_peer_copy(const void* src, int64_t bytes, void* const* dst, int n, void* stream) {
+  SCB_CHECK_ARG(src && dst && n >= 0 && bytes >= 0, SCB_E_ARG, "peer_copy: bad argument");
+  for (int k = 0; k < n; ++k) {
+    const cudaError_t e = cudaMemcpyAsync(dst[k], src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+    if (e != cudaSuccess) { scb_set_error("peer_copy (copy %d): %s", k, cudaGetErrorString(e)); return (int)e; }
+  }
+  return 0;
+}
 // receiver side: stream-ordered wait until every rank's shard of the current epoch has landed in my buffer
 extern "C" int scb_peer_wait(const int* epoch, const int* arrived, int world, void* stream) {
   SCB_CHECK_ARG(epoch && arrived && world >= 1 && world <= 32, SCB_E_ARG, "peer_wait: bad argument");
