@@ -88,9 +88,11 @@ class PeerGather:
                     self.ptrs.append(p.value)
         self.view = torch.as_tensor(_Raw(self.base, self.buf_bytes), device=device)
         self.stream = torch.cuda.Stream(device=device)
-        # large shards: the pushes to different peers go out on several streams (several copy engines / NVLink paths at
-        # once: one stream moved a 4 MB shard in ~12 us, i.e. 84 us for 7 peers in sequence)
-        self.fan = [torch.cuda.Stream(device=device) for _ in range(3)] if self.shard >= (1 << 20) and self.world > 2 else []
+        # Optional fan-out of a large shard's pushes over several streams (SCB_PEER_FAN=k extra streams).  Off by default:
+        # measured at 8 GPUs it made the step slower (1.32 ms vs 1.26 ms with one stream per role), the extra fork / join
+        # events cost more than the parallel copies save at 4 MB per peer.
+        nfan = int(os.environ.get("SCB_PEER_FAN", "0"))
+        self.fan = [torch.cuda.Stream(device=device) for _ in range(nfan)] if self.shard >= (1 << 20) and self.world > 2 else []
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         i64 = dict(dtype=torch.int64, device=device)
         self.arrived_words = torch.tensor([p + self.arr_off + 4 * self.rank for p in self.ptrs], **i64)
