@@ -50,8 +50,12 @@ extern "C" {
 
 /* ABI revision of this header.  scb_version() returns the revision the loaded library was BUILT against; a binding
  * must refuse a library whose revision differs (argument lists may have changed). */
-#define SCB_ABI_VERSION 200
+#define SCB_ABI_VERSION 201
 int scb_version(void);
+/* Device-resident temperature.  Every entry that takes the logit scale 1/tau as a host float (`scale`, and the
+ * coefficients derived from it) also takes `const float* scale_dev` as its last argument before the stream: when non-NULL
+ * the effective scale is scale * (*scale_dev), read on the device -- pass scale = 1 and a pointer to 1/tau.  Nothing then
+ * synchronises with the host, and a captured CUDA graph follows a temperature that changes between replays. */
 const char* scb_last_error(void);
 /* Launch plan of a B x B pass with nA rows against nB columns (host-only arithmetic, no CUDA call):
  * *jparts = how many contiguous parts the column sweep is split into so that the work items fill
@@ -115,7 +119,7 @@ int scb_sum(const float* x, int64_t n, float* scratch, float* out, void* stream)
  * log_softmax inside F.cross_entropy at :127/:129; call with (I,T) for rows and (T,I)
  * for columns).  Writes part_m/part_l [jparts*nsub][nA] (log2-domain running max and sum). */
 int scb_lse_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
-                 int dtype, float scale, int jparts, float* part_m, float* part_l, int path, void* stream);
+                 int dtype, float scale, int jparts, float* part_m, float* part_l, int path, const float* scale_dev, void* stream);
 /* lse[i] = natural-log LSE from nparts partials. */
 int scb_lse_combine(const float* part_m, const float* part_l, int nparts, int64_t n, float* lse, void* stream);
 
@@ -128,7 +132,7 @@ int scb_lse_combine(const float* part_m, const float* part_l, int nparts, int64_
  * THE DEVICE (flag = 1: not guaranteed) and scb_lse_pass_cond / scb_lse_combine_cond run the exact second sweep only
  * when that flag is set -- no host synchronisation, CUDA-graph capturable. */
 int scb_lse2_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
-                  float scale, int jparts, float* part_m, float* part_l, float* col_ref, float* col_sum, void* stream);
+                  float scale, int jparts, float* part_m, float* part_l, float* col_ref, float* col_sum, const float* scale_dev, void* stream);
 /* lse[j] = natural-log column LSE from the nparts = 4*ceil(nA/128) strip partials. */
 int scb_colstat_combine(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* lse, void* stream);
 /* the same fold kept as a pair: sum over the partials = sum_out[j] * 2^ref_out[j] (log2 domain).  Row-sharded runs
@@ -142,10 +146,10 @@ int scb_colstat_partial(const float* col_ref, const float* col_sum, int nparts, 
 int scb_lse2_fold_ranks(const float* pack, int world, int64_t stride, int64_t n_loc, int64_t off_exact, int64_t off_ref,
                         int64_t off_sum, const int* flag, float* col_lse, void* stream);
 /* *flag = (2 * scale * log2(e) * max_i |A_i| * max_j |B_j| >= 90) from the squared row norms (scb_row_sqnorm). */
-int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* sqnB, int64_t nB, float scale, int* flag, void* stream);
+int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* sqnB, int64_t nB, float scale, int* flag, const float* scale_dev, void* stream);
 /* scb_lse_pass / scb_lse_combine that do nothing unless *run_flag != 0 (device pointer). */
 int scb_lse_pass_cond(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
-                      float scale, int jparts, float* part_m, float* part_l, const int* run_flag, void* stream);
+                      float scale, int jparts, float* part_m, float* part_l, const int* run_flag, const float* scale_dev, void* stream);
 int scb_lse_combine_cond(const float* part_m, const float* part_l, int nparts, int64_t n, float* lse, const int* run_flag,
                          void* stream);
 
@@ -157,12 +161,12 @@ int scb_lse_combine_cond(const float* part_m, const float* part_l, int nparts, i
  * ws may be NULL. */
 int scb_anchor_grad_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
                          int dtype, float scale, const float* row_lse, const float* col_lse, int64_t diag_off,
-                         int jparts, float* out, float* ws, int path, void* stream);
+                         int jparts, float* out, float* ws, int path, const float* scale_dev, void* stream);
 /* dA[i,:] (+)= s * ( sum_p out[p][i,:] + (e^{sc*diag_i - row_lse_i} + e^{sc*diag_i - col_lse_i} - 2) * V[i,:] ),
  * s = host_scale * (dev_scale ? *dev_scale : 1); V = the paired rows of the other modality. */
 int scb_anchor_grad_finalize(const float* out, int jparts, int64_t n, int D, const void* V, int64_t ldV, int dtype,
                              const float* row_lse, const float* col_lse_rows, const float* diag, float scale,
-                             float host_scale, const float* dev_scale, int accumulate, float* dA, void* stream);
+                             float host_scale, const float* dev_scale, int accumulate, float* dA, const float* scale_dev, void* stream);
 
 /* Single-pass L_unif forward+backward core (sparsify_clip.py:159-164; replaces torch.pdist,
  * the 7 element-wise passes over its output and _pdist_backward):
@@ -198,7 +202,7 @@ int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, int64_t ldX
                      const float* diag, float scale, float a_coef, const float* u_out, int u_jparts,
                      const float* rq, int rq_parts, float u_coef, const float* u_dev_coef, float l_coef,
                      const float* extra, float e_coef, const float* dev_scale, void* dX, int out_dtype,
-                     int64_t ldOut, void* stream);
+                     int64_t ldOut, const float* scale_dev, void* stream);
 
 /* Scalar assembly of the composed loss (the additions of the ladder, sparsify_clip.py:778-938, on the partial sums):
  * parts = [sum_i row_lse, sum_j col_lse, sum_i I_i.T_i, sum_i |I_i - T_i|^2, rs(img), rs(txt), rs(cen)] (device),
@@ -207,7 +211,7 @@ int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, int64_t ldX
  * c_anchor = w_anchor / 2B, two_scale = 2 / tau, c_align = w_align / B, pair_norm = B (B - 1) / 2; a zero weight
  * skips its term.  One launch instead of ~20 one-element element-wise launches of the host framework. */
 int scb_loss_assemble(const float* parts, float c_anchor, float two_scale, float c_align, float w_unif_img,
-                      float w_unif_txt, float w_unif_cen, float pair_norm, float* loss, float* inv_ssum, void* stream);
+                      float w_unif_txt, float w_unif_cen, float pair_norm, float* loss, float* inv_ssum, const float* scale_dev, void* stream);
 
 /* sparsify_loss (sparsify_clip.py:166-176), forward: row partial sums of
  * (x_i.x_j - (2 delta_ij - 1))^2 over j; rs [jparts*nsub][nR]. */

@@ -31,24 +31,24 @@ SIGNATURES = {
     "scb_normalize_fwd": [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _vp, _vp],
     "scb_normalize_bwd": [_vp, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp],
     "scb_sum": [_vp, _i64, _vp, _vp, _vp],
-    "scb_lse_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _i32, _vp],
+    "scb_lse_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _i32, _vp, _vp],
     "scb_lse_combine": [_vp, _vp, _i32, _i64, _vp, _vp],
-    "scb_lse2_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "scb_lse2_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
     "scb_colstat_combine": [_vp, _vp, _i32, _i64, _vp, _vp],
     "scb_colstat_partial": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
-    "scb_lse2_spread_flag": [_vp, _i64, _vp, _i64, _f32, _vp, _vp],
-    "scb_lse_pass_cond": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp],
+    "scb_lse2_spread_flag": [_vp, _i64, _vp, _i64, _f32, _vp, _vp, _vp],
+    "scb_lse_pass_cond": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp],
     "scb_lse_combine_cond": [_vp, _vp, _i32, _i64, _vp, _vp, _vp],
-    "scb_anchor_grad_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp],
-    "scb_anchor_grad_finalize": [_vp, _i32, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i32, _vp, _vp],
+    "scb_anchor_grad_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp],
+    "scb_anchor_grad_finalize": [_vp, _i32, _i64, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i32, _vp, _vp, _vp],
     "scb_lunif_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp],
     "scb_lunif_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _vp, _i64, _i32, _vp, _i32, _vp],
     "scb_lunif_grad_finalize": [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _i64, _i32, _f32, _vp, _i32, _vp, _vp],
     "scb_debug_pair_trace": [_vp],
-    "scb_loss_assemble": [_vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "scb_loss_assemble": [_vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],
     "scb_lse2_fold_ranks": [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp],
     "scb_grad_combine": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i32, _vp, _i32,
-                         _f32, _vp, _f32, _vp, _f32, _vp, _vp, _i32, _i64, _vp],
+                         _f32, _vp, _f32, _vp, _f32, _vp, _vp, _i32, _i64, _vp, _vp],
     "scb_sparsify_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _i64, _i32, _vp, _i32, _vp],
     "scb_col_sum": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _i32, _vp, _vp],
     "scb_gram_dd": [_vp, _i64, _i32, _i64, _i32, _vp, _f32, _vp, _i32, _vp, _vp],

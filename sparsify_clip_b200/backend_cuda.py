@@ -276,8 +276,9 @@ class CudaBackend:
         return dX
 
     # ------------------------------------------------------------------ B x B passes
-    def lse(self, A, Ball, scale):
-        """Natural-log row LSE of scale * A @ Ball^T -> [nA] fp32."""
+    def lse(self, A, Ball, scale, scale_dev=None):
+        """Natural-log row LSE of scale * A @ Ball^T -> [nA] fp32.  (`scale_dev`, here and below: optional one-element
+        device tensor multiplying `scale` on the device -- 1/tau of a device-resident temperature, no host sync.)"""
         nA, D = A.shape
         nB = Ball.shape[0]
         path = self.path_for(A, Ball)
@@ -288,12 +289,12 @@ class CudaBackend:
         with _On(A.device):
             with self._Timed(self, "lse"):
                 check(self.lib.scb_lse_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0), _DT[A.dtype],
-                                            float(scale), jp, _ptr(pm), _ptr(pl), path, self._stream()), "lse_pass")
+                                            float(scale), jp, _ptr(pm), _ptr(pl), path, _ptr(scale_dev), self._stream()), "lse_pass")
             self._count(2)
             check(self.lib.scb_lse_combine(_ptr(pm), _ptr(pl), jp * nsub, nA, _ptr(out), self._stream()), "lse_combine")
         return out
 
-    def lse_rows_cols(self, A, Bm, scale):
+    def lse_rows_cols(self, A, Bm, scale, scale_dev=None):
         """(row LSE [nA], column LSE [nB]) of scale * A @ Bm^T.  Tensor-core path: ONE sweep (scb_lse2_pass) gives
         both; the exact second sweep over Bm @ A^T is launched conditionally on a device-side norm bound (it returns
         at once for unit-norm rows at tau >= 0.033).  Other paths: two sweeps."""
@@ -301,7 +302,7 @@ class CudaBackend:
         nB = Bm.shape[0]
         path = self.path_for(A, Bm)
         if path != PATH_TC:
-            return self.lse(A, Bm, scale), self.lse(Bm, A, scale)
+            return self.lse(A, Bm, scale, scale_dev), self.lse(Bm, A, scale, scale_dev)
         dev = A.device
         jp, nsub = self._plan(path, nA, nB, D, False, dev)
         jp2, nsub2 = self._plan(path, nB, nA, D, False, dev)
@@ -316,21 +317,24 @@ class CudaBackend:
         sqa, sqb = self.row_sqnorm(A), self.row_sqnorm(Bm)
         st = self._stream()
         with _On(dev):
-            check(self.lib.scb_lse2_spread_flag(_ptr(sqa), nA, _ptr(sqb), nB, float(scale), _ptr(flag), st), "lse2_spread_flag")
+            check(self.lib.scb_lse2_spread_flag(_ptr(sqa), nA, _ptr(sqb), nB, float(scale), _ptr(flag), _ptr(scale_dev), st),
+                  "lse2_spread_flag")
             with self._Timed(self, "lse"):
                 check(self.lib.scb_lse2_pass(_ptr(A), nA, _ptr(Bm), nB, D, A.stride(0), Bm.stride(0), _DT[A.dtype],
-                                             float(scale), jp, _ptr(pm), _ptr(pl), _ptr(cref), _ptr(csum), st), "lse2_pass")
+                                             float(scale), jp, _ptr(pm), _ptr(pl), _ptr(cref), _ptr(csum), _ptr(scale_dev), st),
+                      "lse2_pass")
             check(self.lib.scb_lse_combine(_ptr(pm), _ptr(pl), jp * nsub, nA, _ptr(r), st), "lse_combine")
             check(self.lib.scb_colstat_combine(_ptr(cref), _ptr(csum), n_strips, nB, _ptr(c), st), "colstat_combine")
             with self._Timed(self, "lse"):
                 check(self.lib.scb_lse_pass_cond(_ptr(Bm), nB, _ptr(A), nA, D, Bm.stride(0), A.stride(0), _DT[A.dtype],
-                                                 float(scale), jp2, _ptr(pm2), _ptr(pl2), _ptr(flag), st), "lse_pass_cond")
+                                                 float(scale), jp2, _ptr(pm2), _ptr(pl2), _ptr(flag), _ptr(scale_dev), st),
+                      "lse_pass_cond")
             check(self.lib.scb_lse_combine_cond(_ptr(pm2), _ptr(pl2), jp2 * nsub2, nB, _ptr(c), _ptr(flag), st),
                   "lse_combine_cond")
         self._count(6)
         return r, c
 
-    def lse_rows_colparts(self, A, Bm_all, Bm_rows, A_all, scale):
+    def lse_rows_colparts(self, A, Bm_all, Bm_rows, A_all, scale, scale_dev=None):
         """Row-sharded variant of lse_rows_cols.  A = my rows, Bm_all = all columns, Bm_rows = my rows of the column
         side, A_all = all rows.  Returns None off the tensor-core path, else
         (r [nA], M [nB], L [nB], c_exact_rows [nA], flag): column partial over MY rows = L * 2^M (log2 domain);
@@ -357,17 +361,18 @@ class CudaBackend:
         sqa, sqb = self.row_sqnorm(A_all), self.row_sqnorm(Bm_all)
         st = self._stream()
         with _On(dev):
-            check(self.lib.scb_lse2_spread_flag(_ptr(sqa), A_all.shape[0], _ptr(sqb), nB, float(scale), _ptr(flag), st),
-                  "lse2_spread_flag")
+            check(self.lib.scb_lse2_spread_flag(_ptr(sqa), A_all.shape[0], _ptr(sqb), nB, float(scale), _ptr(flag),
+                                                _ptr(scale_dev), st), "lse2_spread_flag")
             with self._Timed(self, "lse"):
                 check(self.lib.scb_lse2_pass(_ptr(A), nA, _ptr(Bm_all), nB, D, A.stride(0), Bm_all.stride(0), _DT[A.dtype],
-                                             float(scale), jp, _ptr(pm), _ptr(pl), _ptr(cref), _ptr(csum), st), "lse2_pass")
+                                             float(scale), jp, _ptr(pm), _ptr(pl), _ptr(cref), _ptr(csum), _ptr(scale_dev), st),
+                      "lse2_pass")
             check(self.lib.scb_lse_combine(_ptr(pm), _ptr(pl), jp * nsub, nA, _ptr(r), st), "lse_combine")
             check(self.lib.scb_colstat_partial(_ptr(cref), _ptr(csum), n_strips, nB, _ptr(M), _ptr(L), st), "colstat_partial")
             with self._Timed(self, "lse"):
                 check(self.lib.scb_lse_pass_cond(_ptr(Bm_rows), nR, _ptr(A_all), A_all.shape[0], D, Bm_rows.stride(0),
                                                  A_all.stride(0), _DT[A.dtype], float(scale), jp2, _ptr(pm2), _ptr(pl2),
-                                                 _ptr(flag), st), "lse_pass_cond")
+                                                 _ptr(flag), _ptr(scale_dev), st), "lse_pass_cond")
             check(self.lib.scb_lse_combine_cond(_ptr(pm2), _ptr(pl2), jp2 * nsub2, nR, _ptr(c_exact), _ptr(flag), st),
                   "lse_combine_cond")
         self._count(6)
@@ -386,7 +391,7 @@ class CudaBackend:
         return out
 
     def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off,
-                    host_scale, dev_scale, want_ws):
+                    host_scale, dev_scale, want_ws, scale_dev=None):
         """dA = s * [ sum_j (P_ij + Q_ij) Ball_j  (j != diagonal)  +  (P_ii + Q_ii - 2) V_i ]  (fp32 [nA, D]);
         ws = sum_ij (P+Q)_ij (A_i . Ball_j) as a 0-dim tensor (for d/dtau) when want_ws."""
         nA, D = A.shape
@@ -400,16 +405,16 @@ class CudaBackend:
             with self._Timed(self, "anchor_grad"):
                 check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0),
                                                     _DT[A.dtype], float(scale), _ptr(row_lse), _ptr(col_lse_all),
-                                                    int(diag_off), jp, _ptr(out), _ptr(ws), path, self._stream()),
-                      "anchor_grad_pass")
+                                                    int(diag_off), jp, _ptr(out), _ptr(ws), path, _ptr(scale_dev),
+                                                    self._stream()), "anchor_grad_pass")
             self._count(2)
             check(self.lib.scb_anchor_grad_finalize(_ptr(out), jp, nA, D, _ptr(V_rows), V_rows.stride(0), _DT[V_rows.dtype],
                                                     _ptr(row_lse), _ptr(col_lse_rows), _ptr(diag), float(scale),
-                                                    float(host_scale), _ptr(dev_scale), 0, _ptr(dA), self._stream()),
-                  "anchor_grad_finalize")
+                                                    float(host_scale), _ptr(dev_scale), 0, _ptr(dA), _ptr(scale_dev),
+                                                    self._stream()), "anchor_grad_finalize")
         return dA, (self.sum(ws) if want_ws else None)
 
-    def anchor_grad_pass(self, A, Ball, scale, row_lse, col_lse_all, diag_off, want_ws):
+    def anchor_grad_pass(self, A, Ball, scale, row_lse, col_lse_all, diag_off, want_ws, scale_dev=None):
         """The recompute sweep alone (no finaliser): {'out': [jparts, nA, D] fp32 partials, 'jparts', 'ws': 0-dim or None}."""
         nA, D = A.shape
         nB = Ball.shape[0]
@@ -421,8 +426,8 @@ class CudaBackend:
             with self._Timed(self, "anchor_grad"):
                 check(self.lib.scb_anchor_grad_pass(_ptr(A), nA, _ptr(Ball), nB, D, A.stride(0), Ball.stride(0),
                                                     _DT[A.dtype], float(scale), _ptr(row_lse), _ptr(col_lse_all),
-                                                    int(diag_off), jp, _ptr(out), _ptr(ws), path, self._stream()),
-                      "anchor_grad_pass")
+                                                    int(diag_off), jp, _ptr(out), _ptr(ws), path, _ptr(scale_dev),
+                                                    self._stream()), "anchor_grad_pass")
         self._count()
         return {"out": out, "jparts": jp, "ws": self.sum(ws) if want_ws else None}
 
@@ -443,18 +448,19 @@ class CudaBackend:
                 _ptr(a.get("diag")), float(a.get("scale", 0.0)), float(a.get("coef", 0.0)),
                 _ptr(core.get("U")), int(core.get("jparts", 0)), _ptr(core.get("rq")), int(core.get("nparts", 0)),
                 float(u.get("coef", 0.0)), _ptr(u.get("dev_coef")), float(l_coef), _ptr(extra), float(e_coef),
-                _ptr(dev_scale), _ptr(dX), _DT[out_dtype], dX.stride(0), self._stream()), "grad_combine")
+                _ptr(dev_scale), _ptr(dX), _DT[out_dtype], dX.stride(0), _ptr(a.get("scale_dev")), self._stream()),
+                "grad_combine")
         self._count()
         return dX
 
-    def loss_assemble(self, parts, c_anchor, two_scale, c_align, w_img, w_txt, w_cen, pair_norm):
+    def loss_assemble(self, parts, c_anchor, two_scale, c_align, w_img, w_txt, w_cen, pair_norm, scale_dev=None):
         """(loss 0-dim, inv_ssum [3]) from the partial sums (scb_loss_assemble)."""
         loss = _empty((), dtype=torch.float32, device=parts.device)
         inv = _empty(3, dtype=torch.float32, device=parts.device)
         with _On(parts.device):
             check(self.lib.scb_loss_assemble(_ptr(parts), float(c_anchor), float(two_scale), float(c_align), float(w_img),
                                              float(w_txt), float(w_cen), float(pair_norm), _ptr(loss), _ptr(inv),
-                                             self._stream()), "loss_assemble")
+                                             _ptr(scale_dev), self._stream()), "loss_assemble")
         self._count()
         return loss, inv
 

@@ -2,18 +2,19 @@
 // argument validation and dispatch to the SIMT (simt_pass.cu) or tensor-core (tc_pass.cu) path.
 #include "common.cuh"
 
-int scb_simt_lse(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, cudaStream_t);
+int scb_simt_lse(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, const float*,
+                 cudaStream_t);
 int scb_simt_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*,
-                         const float*, int64_t, int, float*, float*, cudaStream_t);
+                         const float*, int64_t, int, float*, float*, const float*, cudaStream_t);
 int scb_simt_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
                    int64_t, int, float*, float*, float*, cudaStream_t);
 int scb_simt_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
 int scb_tc_lse(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, const int*,
-               cudaStream_t);
+               const float*, cudaStream_t);
 int scb_tc_lse2(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, int, float*, float*, float*, float*,
-                cudaStream_t);
+                const float*, cudaStream_t);
 int scb_tc_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
-                       int64_t, int, float*, float*, cudaStream_t);
+                       int64_t, int, float*, float*, const float*, cudaStream_t);
 int scb_tc_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*, int64_t,
                  int, float*, float*, float*, cudaStream_t);
 int scb_tc_sparsify_sum(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, int64_t, int, float*, cudaStream_t);
@@ -90,44 +91,47 @@ extern "C" int scb_grad_kernel_kind(int64_t nA, int D, int n_sm, int* units) {
 }
 
 extern "C" int scb_lse_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
-                            float scale, int jparts, float* part_m, float* part_l, int path, void* stream) {
+                            float scale, int jparts, float* part_m, float* part_l, int path, const float* scale_dev,
+                            void* stream) {
   SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path);
   SCB_CHECK_ARG((part_m && part_l) || nA == 0, SCB_E_ARG, "lse_pass: null output");
   SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "lse_pass: needs scale > 0 and nB > 0");
   cudaStream_t s = (cudaStream_t)stream;
-  return path == SCB_PATH_TC ? scb_tc_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, nullptr, s)
-                             : scb_simt_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, s);
+  return path == SCB_PATH_TC ? scb_tc_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, nullptr, scale_dev, s)
+                             : scb_simt_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, scale_dev, s);
 }
 
 // the same sweep launched conditionally: the kernel returns at once unless *run_flag != 0 (tensor-core path only)
 extern "C" int scb_lse_pass_cond(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
                                  int dtype, float scale, int jparts, float* part_m, float* part_l, const int* run_flag,
-                                 void* stream) {
+                                 const float* scale_dev, void* stream) {
   SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, SCB_PATH_TC);
   SCB_CHECK_ARG((part_m && part_l && run_flag) || nA == 0, SCB_E_ARG, "lse_pass_cond: null argument");
   SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "lse_pass_cond: needs scale > 0 and nB > 0");
-  return scb_tc_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, run_flag, (cudaStream_t)stream);
+  return scb_tc_lse(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, run_flag, scale_dev, (cudaStream_t)stream);
 }
 
 extern "C" int scb_lse2_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                              float scale, int jparts, float* part_m, float* part_l, float* col_ref, float* col_sum,
-                             void* stream) {
+                             const float* scale_dev, void* stream) {
   SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, SCB_PATH_TC);
   SCB_CHECK_ARG((part_m && part_l && col_ref && col_sum) || nA == 0, SCB_E_ARG, "lse2_pass: null output");
   SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "lse2_pass: needs scale > 0 and nB > 0");
-  return scb_tc_lse2(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, col_ref, col_sum, (cudaStream_t)stream);
+  return scb_tc_lse2(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, jparts, part_m, part_l, col_ref, col_sum, scale_dev,
+                     (cudaStream_t)stream);
 }
 
 extern "C" int scb_anchor_grad_pass(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB,
                                     int dtype, float scale, const float* row_lse, const float* col_lse, int64_t diag_off,
-                                    int jparts, float* out, float* ws, int path, void* stream) {
+                                    int jparts, float* out, float* ws, int path, const float* scale_dev, void* stream) {
   SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path);
   SCB_CHECK_ARG((row_lse && col_lse && out) || nA == 0, SCB_E_ARG, "anchor_grad_pass: null argument");
   SCB_CHECK_ARG(scale > 0.f && nB > 0, SCB_E_ARG, "anchor_grad_pass: needs scale > 0 and nB > 0");
   cudaStream_t s = (cudaStream_t)stream;
   return path == SCB_PATH_TC
-             ? scb_tc_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s)
-             : scb_simt_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s);
+             ? scb_tc_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, scale_dev, s)
+             : scb_simt_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, scale_dev,
+                                    s);
 }
 
 extern "C" int scb_lunif_pass(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,

@@ -241,36 +241,57 @@ __global__ void __launch_bounds__(256) k_lse_combine_cond(const float* __restric
 template <bool FINAL>
 __global__ void __launch_bounds__(256) k_colstat_fold(const float* __restrict__ cref, const float* __restrict__ csum, int nparts,
                                                       int64_t n, float* __restrict__ out0, float* __restrict__ out1) {
-  __shared__ float shM[8][32], shL[8][32];
+  // one block = 128 columns: every lane owns 4 consecutive columns (one 16-byte load per partial row when the layout
+  // allows: 512 contiguous bytes per warp and row instead of 128), the 8 warps split the partial rows
+  __shared__ float shM[8][128], shL[8][128];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t j = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t j0 = (int64_t)blockIdx.x * 128 + lane * 4;
   const int64_t nref = (n + 31) / 32;
-  float M = -INFINITY, L = 0.f;
-  if (j < n) {
+  const int64_t rcol = j0 >> 5;                       // the 4 columns of a lane share one 32-column reference block
+  const bool vec = (n % 4 == 0) && (j0 + 3 < n);
+  float M[4], L[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { M[c] = -INFINITY; L[c] = 0.f; }
+  if (j0 < n) {
     for (int p = w; p < nparts; p += 8) {
-      const float r = __ldg(cref + (int64_t)p * nref + blockIdx.x);
-      const float v = __ldcs(csum + (int64_t)p * n + j);
-      if (r == -INFINITY || v == 0.f) continue;
-      if (r > M) { L *= exp2f(M - r); M = r; }
-      L += v * exp2f(r - M);
+      const float r = __ldg(cref + (int64_t)p * nref + rcol);
+      float v[4];
+      if (vec) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(csum + (int64_t)p * n + j0));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = (j0 + c < n) ? __ldcs(csum + (int64_t)p * n + j0 + c) : 0.f;
+      }
+      if (r == -INFINITY) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (v[c] == 0.f) continue;
+        if (r > M[c]) { L[c] *= exp2f(M[c] - r); M[c] = r; }
+        L[c] += v[c] * exp2f(r - M[c]);
+      }
     }
   }
-  shM[w][lane] = M;
-  shL[w][lane] = L;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { shM[w][lane * 4 + c] = M[c]; shL[w][lane * 4 + c] = L[c]; }
   __syncthreads();
-  if (w == 0 && j < n) {
-    float Mx = -INFINITY;
+  if (threadIdx.x < 128) {
+    const int col = threadIdx.x;
+    const int64_t j = (int64_t)blockIdx.x * 128 + col;
+    if (j < n) {
+      float Mx = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) Mx = fmaxf(Mx, shM[k][lane]);
-    float Ls = 0.f;
+      for (int k = 0; k < 8; ++k) Mx = fmaxf(Mx, shM[k][col]);
+      float Ls = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (shM[k][lane] != -INFINITY) Ls += shL[k][lane] * exp2f(shM[k][lane] - Mx);
-    if (FINAL) {
-      out0[j] = (Mx + log2f(Ls)) * SCB_LN2;
-    } else {
-      out0[j] = Mx;
-      out1[j] = Ls;
+      for (int k = 0; k < 8; ++k)
+        if (shM[k][col] != -INFINITY) Ls += shL[k][col] * exp2f(shM[k][col] - Mx);
+      if (FINAL) {
+        out0[j] = (Mx + log2f(Ls)) * SCB_LN2;
+      } else {
+        out0[j] = Mx;
+        out1[j] = Ls;
+      }
     }
   }
 }
@@ -278,9 +299,10 @@ __global__ void __launch_bounds__(256) k_colstat_fold(const float* __restrict__ 
 // Scalar assembly of the composed loss from the step's partial sums (one thread; replaces ~20 one-element
 // element-wise launches of the host framework per step).  p = [sum r, sum c, sum diag, sum |x-y|^2, rsI, rsT, rsC].
 __global__ void k_loss_assemble(const float* __restrict__ p, float ca, float two_scale, float cl, float wi, float wt, float wc,
-                                float pair_norm, float* __restrict__ loss, float* __restrict__ inv_ssum) {
+                                float pair_norm, float* __restrict__ loss, float* __restrict__ inv_ssum,
+                                const float* __restrict__ scale_dev) {
   float L = 0.f;
-  if (ca != 0.f) L += ca * (p[0] + p[1] - two_scale * p[2]);
+  if (ca != 0.f) L += ca * (p[0] + p[1] - eff_scale(two_scale, scale_dev) * p[2]);
   if (cl != 0.f) L += cl * p[3];
   const float w[3] = {wi, wt, wc};
 #pragma unroll
@@ -320,7 +342,8 @@ __global__ void __launch_bounds__(256) k_fold_ranks(const float* __restrict__ pa
 // flag = 1 when the logits can spread by more than `bound` (log2 units) inside one block of the fused pass:
 // 2 * scale * log2e * max_i |a_i| * max_j |b_j| >= bound   (sqn = squared row norms)
 __global__ void __launch_bounds__(1024) k_spread_flag(const float* __restrict__ sqnA, int64_t nA, const float* __restrict__ sqnB,
-                                                      int64_t nB, float scale, float bound, int* __restrict__ flag) {
+                                                      int64_t nB, float scale, const float* __restrict__ scale_dev, float bound,
+                                                      int* __restrict__ flag) {
   __shared__ float sh[2][32];
   float ma = 0.f, mb = 0.f;
   for (int64_t i = threadIdx.x; i < nA; i += 1024) ma = fmaxf(ma, sqnA[i]);
@@ -331,7 +354,7 @@ __global__ void __launch_bounds__(1024) k_spread_flag(const float* __restrict__ 
   if (threadIdx.x < 32) {
     ma = scb_warp_max(sh[0][threadIdx.x]); mb = scb_warp_max(sh[1][threadIdx.x]);
     if (threadIdx.x == 0) {
-      const float spread = 2.f * scale * SCB_LOG2E * sqrtf(ma) * sqrtf(mb);
+      const float spread = 2.f * eff_scale(scale, scale_dev) * SCB_LOG2E * sqrtf(ma) * sqrtf(mb);
       *flag = (spread >= bound || !(spread == spread)) ? 1 : 0;      // NaN/inf norms -> take the exact sweep
     }
   }
@@ -346,12 +369,13 @@ __global__ void __launch_bounds__(kThreads) k_anchor_fin(const float* __restrict
                                                          const float* __restrict__ col_lse_rows,
                                                          const float* __restrict__ diag, float scale, float host_scale,
                                                          const float* __restrict__ dev_scale, int accumulate,
-                                                         float* __restrict__ dA) {
+                                                         float* __restrict__ dA, const float* __restrict__ scale_dev) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (row >= n) return;
-  const float s = eff_scale(host_scale, dev_scale);
-  const float sii = scale * diag[row];
+  const float sd = scale_dev ? __ldg(scale_dev) : 1.f;       // a device-resident 1/tau multiplies both uses of the scale
+  const float s = eff_scale(host_scale, dev_scale) * sd;
+  const float sii = scale * sd * diag[row];
   const float dcoef = expf(sii - row_lse[row]) + expf(sii - col_lse_rows[row]) - 2.f;
   for_row<VEC, false>(V, ldV, nullptr, 0, dtype, row, D, lane, [&](int d, float(&a)[8], float(&)[8], int nv) {
 #pragma unroll
@@ -409,6 +433,7 @@ struct CombineArgs {
   const float* extra; float e_coef;
   const float* dev_scale;
   void* dX; int out_dtype; int64_t ldOut;
+  const float* scale_dev;      // optional device multiplier of `scale` and `a_coef` (1/tau of a device-resident temperature)
 };
 
 template <bool VEC>
@@ -432,7 +457,8 @@ __global__ void __launch_bounds__(256) k_grad_combine(const CombineArgs a) {
   for (int i = 0; i < W; ++i) g[i] = a.l_coef != 0.f ? a.l_coef * (x[i] - y[i]) : 0.f;
   const int64_t o = row * (int64_t)a.D + d;
   if (a.a_out) {
-    const float sii = a.scale * __ldg(a.diag + row);
+    const float sd = a.scale_dev ? __ldg(a.scale_dev) : 1.f;
+    const float sii = a.scale * sd * __ldg(a.diag + row);
     const float dcoef = expf(sii - __ldg(a.row_lse + row)) + expf(sii - __ldg(a.col_lse_rows + row)) - 2.f;
     float acc[8];
 #pragma unroll
@@ -448,7 +474,7 @@ __global__ void __launch_bounds__(256) k_grad_combine(const CombineArgs a) {
       }
     }
 #pragma unroll
-    for (int i = 0; i < W; ++i) g[i] = fmaf(a.a_coef, acc[i], g[i]);
+    for (int i = 0; i < W; ++i) g[i] = fmaf(a.a_coef * sd, acc[i], g[i]);
   }
   if (a.u_out) {
     const float uc = a.u_dev_coef ? a.u_coef * __ldg(a.u_dev_coef) : a.u_coef;
@@ -628,15 +654,15 @@ extern "C" int scb_lse_combine(const float* part_m, const float* part_l, int npa
 
 extern "C" int scb_anchor_grad_finalize(const float* out, int jparts, int64_t n, int D, const void* V, int64_t ldV, int dtype,
                                         const float* row_lse, const float* col_lse_rows, const float* diag, float scale,
-                                        float host_scale, const float* dev_scale, int accumulate, float* dA, void* stream) {
+                                        float host_scale, const float* dev_scale, int accumulate, float* dA, const float* scale_dev, void* stream) {
   SCB_COMMON_CHECKS(out && V && row_lse && col_lse_rows && diag && dA, n, D, dtype);
   SCB_CHECK_ARG(jparts > 0, SCB_E_ARG, "anchor_grad_finalize: jparts");
   if (n == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (vec_ok(V, ldV, D))
-    k_anchor_fin<true><<<row_grid(n), kThreads, 0, s>>>(out, jparts, n, D, V, ldV, dtype, row_lse, col_lse_rows, diag, scale, host_scale, dev_scale, accumulate, dA);
+    k_anchor_fin<true><<<row_grid(n), kThreads, 0, s>>>(out, jparts, n, D, V, ldV, dtype, row_lse, col_lse_rows, diag, scale, host_scale, dev_scale, accumulate, dA, scale_dev);
   else
-    k_anchor_fin<false><<<row_grid(n), kThreads, 0, s>>>(out, jparts, n, D, V, ldV, dtype, row_lse, col_lse_rows, diag, scale, host_scale, dev_scale, accumulate, dA);
+    k_anchor_fin<false><<<row_grid(n), kThreads, 0, s>>>(out, jparts, n, D, V, ldV, dtype, row_lse, col_lse_rows, diag, scale, host_scale, dev_scale, accumulate, dA, scale_dev);
   SCB_CHECK_LAUNCH("anchor_grad_finalize");
   return 0;
 }
@@ -661,7 +687,7 @@ extern "C" int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, 
                                 const float* diag, float scale, float a_coef, const float* u_out, int u_jparts,
                                 const float* rq, int rq_parts, float u_coef, const float* u_dev_coef, float l_coef,
                                 const float* extra, float e_coef, const float* dev_scale, void* dX, int out_dtype,
-                                int64_t ldOut, void* stream) {
+                                int64_t ldOut, const float* scale_dev, void* stream) {
   SCB_COMMON_CHECKS(X && dX, n, D, dtype);
   SCB_CHECK_ARG(scb_dtype_ok(out_dtype) && ldOut >= D, SCB_E_ARG, "grad_combine: bad output layout");
   SCB_CHECK_ARG(!a_out || (Y && row_lse && col_lse_rows && diag && a_jparts > 0), SCB_E_ARG, "grad_combine: anchor term");
@@ -669,7 +695,7 @@ extern "C" int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, 
   SCB_CHECK_ARG(l_coef == 0.f || Y, SCB_E_ARG, "grad_combine: L_align term needs Y");
   if (n == 0) return 0;
   CombineArgs a{X, Y, n, D, ldX, ldY, dtype, a_out, a_jparts, row_lse, col_lse_rows, diag, scale, a_coef, u_out, u_jparts,
-                rq, rq_parts, u_coef, u_dev_coef, l_coef, extra, e_coef, dev_scale, dX, out_dtype, ldOut};
+                rq, rq_parts, u_coef, u_dev_coef, l_coef, extra, e_coef, dev_scale, dX, out_dtype, ldOut, scale_dev};
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = vec_ok(X, ldX, D) && (!Y || vec_ok(Y, ldY, D)) && scb_aligned16(dX) && ldOut % 8 == 0 &&
                    (!extra || scb_aligned16(extra));
@@ -694,25 +720,25 @@ extern "C" int scb_lse_combine_cond(const float* part_m, const float* part_l, in
 extern "C" int scb_colstat_combine(const float* col_ref, const float* col_sum, int nparts, int64_t n, float* lse, void* stream) {
   SCB_CHECK_ARG(col_ref && col_sum && lse && nparts > 0 && n >= 0, SCB_E_ARG, "colstat_combine: bad argument");
   if (n == 0) return 0;
-  k_colstat_fold<true><<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, lse, nullptr);
+  k_colstat_fold<true><<<(unsigned)((n + 127) / 128), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, lse, nullptr);
   SCB_CHECK_LAUNCH("colstat_combine");
   return 0;
 }
 
 extern "C" int scb_lse2_spread_flag(const float* sqnA, int64_t nA, const float* sqnB, int64_t nB, float scale, int* flag,
-                                    void* stream) {
+                                    const float* scale_dev, void* stream) {
   SCB_CHECK_ARG(sqnA && sqnB && flag && nA >= 0 && nB >= 0 && scale > 0.f, SCB_E_ARG, "lse2_spread_flag: bad argument");
-  k_spread_flag<<<1, 1024, 0, (cudaStream_t)stream>>>(sqnA, nA, sqnB, nB, scale, 90.f, flag);
+  k_spread_flag<<<1, 1024, 0, (cudaStream_t)stream>>>(sqnA, nA, sqnB, nB, scale, scale_dev, 90.f, flag);
   SCB_CHECK_LAUNCH("lse2_spread_flag");
   return 0;
 }
 
 extern "C" int scb_loss_assemble(const float* parts, float c_anchor, float two_scale, float c_align, float w_unif_img,
                                  float w_unif_txt, float w_unif_cen, float pair_norm, float* loss, float* inv_ssum,
-                                 void* stream) {
+                                 const float* scale_dev, void* stream) {
   SCB_CHECK_ARG(parts && loss && inv_ssum, SCB_E_ARG, "loss_assemble: bad argument");
   k_loss_assemble<<<1, 1, 0, (cudaStream_t)stream>>>(parts, c_anchor, two_scale, c_align, w_unif_img, w_unif_txt, w_unif_cen,
-                                                     pair_norm, loss, inv_ssum);
+                                                     pair_norm, loss, inv_ssum, scale_dev);
   SCB_CHECK_LAUNCH("loss_assemble");
   return 0;
 }
@@ -735,7 +761,7 @@ extern "C" int scb_colstat_partial(const float* col_ref, const float* col_sum, i
                                    float* sum_out, void* stream) {
   SCB_CHECK_ARG(col_ref && col_sum && ref_out && sum_out && nparts > 0 && n >= 0, SCB_E_ARG, "colstat_partial: bad argument");
   if (n == 0) return 0;
-  k_colstat_fold<false><<<(unsigned)((n + 31) / 32), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, ref_out, sum_out);
+  k_colstat_fold<false><<<(unsigned)((n + 127) / 128), 256, 0, (cudaStream_t)stream>>>(col_ref, col_sum, nparts, n, ref_out, sum_out);
   SCB_CHECK_LAUNCH("colstat_partial");
   return 0;
 }

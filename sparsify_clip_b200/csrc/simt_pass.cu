@@ -23,6 +23,7 @@ struct SimtParams {
   int64_t nA, nB, ldA, ldB;
   int D, dtype, jparts;
   float p0;                 // LSE/anchor: scale*log2e ; lunif: t*log2e
+  const float* p0_dev;      // optional device multiplier of p0 (1/tau of a device-resident temperature)
   const float* rowvec;      // anchor: row lse (natural log) ; lunif: sq norms of the A rows
   const float* colvec;      // anchor: col lse ; lunif: sq norms of the Bm rows
   int64_t diag_off;         // column j is "the diagonal" of local row i when j == i + diag_off
@@ -34,6 +35,7 @@ struct SimtParams {
 template <int MODE>
 __global__ void __launch_bounds__(256) k_simt_pass(const SimtParams P) {
   constexpr bool GRAD = (MODE == M_ANCHOR_GRAD || MODE == M_LUNIF_GRAD);
+  const float p0_eff = P.p0_dev ? P.p0 * __ldg(P.p0_dev) : P.p0;
   __shared__ float As[TR][KC + 1];
   __shared__ float Bs[TJ][KC + 1];
   __shared__ float Ws[GRAD ? TR : 1][TJ + 1];
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(256) k_simt_pass(const SimtParams P) {
       const bool is_diag = (gj == gi + P.diag_off);
       const float g = acc[rr];
       if (MODE == M_LSE) {
-        const float y = jok ? g * P.p0 : -INFINITY;
+        const float y = jok ? g * p0_eff : -INFINITY;
         const float tmax = scb_warp_max(y);
         const float mnew = fmaxf(st0[rr], tmax);
         float e = (mnew == -INFINITY) ? 0.f : exp2f(y - mnew);
@@ -108,13 +110,13 @@ __global__ void __launch_bounds__(256) k_simt_pass(const SimtParams P) {
         st1[rr] = st1[rr] * corr + e;
         st0[rr] = mnew;
       } else if (MODE == M_ANCHOR_GRAD) {
-        const float y = g * P.p0;
+        const float y = g * p0_eff;
         float ww = jok ? (exp2f(y - rowc[rr]) + exp2f(y - colc)) : 0.f;
         st0[rr] += scb_warp_sum(ww * g);           // sum_j w_ij (a_i.b_j), diagonal included
         w[rr] = is_diag ? 0.f : ww;
       } else if (MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM) {
         const float d2 = fmaxf(rowc[rr] + colc - 2.f * g, 0.f);
-        const float ww = (jok && !is_diag) ? exp2f(-P.p0 * d2) : 0.f;
+        const float ww = (jok && !is_diag) ? exp2f(-p0_eff * d2) : 0.f;
         const float s = scb_warp_sum(ww);
         st0[rr] += s;
         st1[rr] += s;
@@ -186,29 +188,29 @@ int launch(const SimtParams& P, cudaStream_t s) {
 
 // entry points used by api.cu -------------------------------------------------------------
 int scb_simt_lse(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
-                 float scale, int jparts, float* pm, float* pl, cudaStream_t s) {
-  SimtParams P{A, Bm, nA, nB, ldA, ldB, D, dtype, jparts, scale * SCB_LOG2E, nullptr, nullptr, INT64_MIN / 2, nullptr, pm, pl};
+                 float scale, int jparts, float* pm, float* pl, const float* scale_dev, cudaStream_t s) {
+  SimtParams P{A, Bm, nA, nB, ldA, ldB, D, dtype, jparts, scale * SCB_LOG2E, scale_dev, nullptr, nullptr, INT64_MIN / 2, nullptr, pm, pl};
   return launch<M_LSE>(P, s);
 }
 int scb_simt_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                          float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts,
-                         float* out, float* ws, cudaStream_t s) {
-  SimtParams P{A, Bm, nA, nB, ldA, ldB, D, dtype, jparts, scale * SCB_LOG2E, row_lse, col_lse, diag_off, out, ws, nullptr};
+                         float* out, float* ws, const float* scale_dev, cudaStream_t s) {
+  SimtParams P{A, Bm, nA, nB, ldA, ldB, D, dtype, jparts, scale * SCB_LOG2E, scale_dev, row_lse, col_lse, diag_off, out, ws, nullptr};
   return launch<M_ANCHOR_GRAD>(P, s);
 }
 int scb_simt_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll, int dtype,
                    float t, const float* sqn_r, const float* sqn_all, int64_t row_offset, int jparts, float* U,
                    float* rq, float* rs, cudaStream_t s) {
-  SimtParams P{Xr, Xall, nR, nAll, ldR, ldAll, D, dtype, jparts, t * SCB_LOG2E, sqn_r, sqn_all, row_offset, U, rq, rs};
+  SimtParams P{Xr, Xall, nR, nAll, ldR, ldAll, D, dtype, jparts, t * SCB_LOG2E, nullptr, sqn_r, sqn_all, row_offset, U, rq, rs};
   return U ? launch<M_LUNIF_GRAD>(P, s) : launch<M_LUNIF_SUM>(P, s);
 }
 int scb_simt_rank_count(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                         const float* gt_score, int64_t diag_off, int jparts, float* cnt, cudaStream_t s) {
-  SimtParams P{A, Bm, nA, nB, ldA, ldB, D, dtype, jparts, 0.f, gt_score, nullptr, diag_off, nullptr, cnt, nullptr};
+  SimtParams P{A, Bm, nA, nB, ldA, ldB, D, dtype, jparts, 0.f, nullptr, gt_score, nullptr, diag_off, nullptr, cnt, nullptr};
   return launch<M_RANK_COUNT>(P, s);
 }
 int scb_simt_sparsify_sum(const void* Xr, int64_t nR, const void* Xall, int64_t nAll, int D, int64_t ldR, int64_t ldAll,
                           int dtype, int64_t row_offset, int jparts, float* rs, cudaStream_t s) {
-  SimtParams P{Xr, Xall, nR, nAll, ldR, ldAll, D, dtype, jparts, 0.f, nullptr, nullptr, row_offset, nullptr, rs, nullptr};
+  SimtParams P{Xr, Xall, nR, nAll, ldR, ldAll, D, dtype, jparts, 0.f, nullptr, nullptr, nullptr, row_offset, nullptr, rs, nullptr};
   return launch<M_SPARSIFY_SUM>(P, s);
 }

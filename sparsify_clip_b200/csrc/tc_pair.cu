@@ -50,6 +50,7 @@ struct PairParams {
   int D, kch, n_rb, n_jb, jparts, nslots, fmt;
   int64_t span;                // tiles of the linearised (row block, column tile) space per CTA pair
   float p0;
+  const float* p0_dev;         // optional device multiplier of p0 (1/tau of a device-resident temperature)
   const float* rowvec;
   const float* colvec;
   int64_t diag_off;
@@ -175,6 +176,7 @@ template <int MODE, int KCH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PairParams P) {
   extern __shared__ uint8_t smem_raw[];
+  const float p0_eff = P.p0_dev ? P.p0 * __ldg(P.p0_dev) : P.p0;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in both CTAs
   const int kch = KCH ? KCH : P.kch;
   const int n_astat = KCH ? (KCH < kAStat ? KCH : kAStat) : min(kch, kAStat);
@@ -450,7 +452,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool row_ok = gi < P.nA;
       float rowc = 0.f;
       if (MODE == M_ANCHOR_GRAD) rowc = row_ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
-      if (MODE == M_LUNIF_GRAD) rowc = row_ok ? P.rowvec[gi] * P.p0 : 0.f;
+      if (MODE == M_LUNIF_GRAD) rowc = row_ok ? P.rowvec[gi] * p0_eff : 0.f;
       float st0 = 0.f, st1 = 0.f;
       const int64_t my_diag_col = gi + P.diag_off;
 
@@ -464,7 +466,7 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (idx < 128) {
             const int64_t gj = (int64_t)jb * 128 + idx;
             float cv = INFINITY;
-            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * P.p0;
+            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * p0_eff;
             cbuf[b * 128 + idx] = cv;
           }
           ptx::named_bar_sync(1, kEpiThreads);
@@ -496,13 +498,13 @@ k_tc_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float g = __uint_as_float(v[c]);
-              const float y = g * P.p0;
+              const float y = g * p0_eff;
               const float ww = scb_ex2(y - rowc) + scb_ex2(y - cb[c]);   // dead columns: 0 + 0
               st0 = fmaf(ww, g, st0);
               w[c] = ww;
             }
           } else {  // lunif: exp2(2 p0 g - p0 n_i - p0 n_j); dead columns carry +inf in cb -> 0
-            const float two_p0 = 2.f * P.p0;
+            const float two_p0 = 2.f * p0_eff;
 #pragma unroll
             for (int c = 0; c < 32; ++c) w[c] = scb_ex2(fmaf(__uint_as_float(v[c]), two_p0, -(rowc + cb[c])));
           }
@@ -744,8 +746,9 @@ int launch_pair(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
 
 int scb_tc_pair_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                             float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts,
-                            float* out, float* ws, cudaStream_t s) {
+                            float* out, float* ws, const float* scale_dev, cudaStream_t s) {
   PairParams P{};
+  P.p0_dev = scale_dev;
   P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.rowvec = row_lse; P.colvec = col_lse; P.diag_off = diag_off;
   P.out = out; P.s0 = ws;
   return launch_pair<M_ANCHOR_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
@@ -762,9 +765,10 @@ int scb_tc_pair_lunif(const void* Xr, int64_t nR, const void* Xall, int64_t nAll
 // A row range of a larger pass on at most `max_pairs` CTA pairs (tc_quad.cu runs it on the SMs that clusters of 4
 // cannot use): `row_base` rows precede A's first row in the pass, `slot_rows` = rows of the whole pass.
 int scb_tc_pair_range(int mode, const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
-                      float p0, const float* rowvec, const float* colvec, int64_t diag_off, int jparts, int64_t slot_rows,
-                      float* out, float* s0, float* s1, int max_pairs, cudaStream_t s) {
+                      float p0, const float* p0_dev, const float* rowvec, const float* colvec, int64_t diag_off, int jparts,
+                      int64_t slot_rows, float* out, float* s0, float* s1, int max_pairs, cudaStream_t s) {
   PairParams P{};
+  P.p0_dev = p0_dev;
   P.jparts = jparts; P.p0 = p0; P.rowvec = rowvec; P.colvec = colvec; P.diag_off = diag_off; P.slot_rows = slot_rows;
   P.out = out; P.s0 = s0; P.s1 = s1;
   return mode == M_ANCHOR_GRAD ? launch_pair<M_ANCHOR_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s, max_pairs)

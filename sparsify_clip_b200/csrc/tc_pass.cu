@@ -49,6 +49,7 @@ struct TcParams {
   int a_stationary, nstage, g_in_tmem, fmt;  // fmt: 1 bf16, 0 fp16 (both MMA operands must share it:
                                              // a mixed-format kind::f16 descriptor is an illegal instruction)
   float p0;                                  // LSE/anchor: scale*log2e ; lunif: t*log2e
+  const float* p0_dev;                       // optional device multiplier of p0 (1/tau of a device-resident temperature)
   const float* rowvec;
   const float* colvec;
   int64_t diag_off;
@@ -99,6 +100,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   constexpr bool NEED_COLVEC = (MODE == M_ANCHOR_GRAD || MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM);
 
   extern __shared__ uint8_t smem_raw[];
+  const float p0_eff = P.p0_dev ? P.p0 * __ldg(P.p0_dev) : P.p0;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = P.a_stationary ? (uint32_t)P.kch * kSlotBytes : 0u;
   const uint32_t sm_a = smem_base;
@@ -330,7 +332,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // per-row constants and running statistics
       float rowc = 0.f;
       if (MODE == M_ANCHOR_GRAD) rowc = row_ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
-      if (MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM) rowc = row_ok ? P.rowvec[gi] * P.p0 : 0.f;
+      if (MODE == M_LUNIF_GRAD || MODE == M_LUNIF_SUM) rowc = row_ok ? P.rowvec[gi] * p0_eff : 0.f;
       if (MODE == M_RANK_COUNT) rowc = row_ok ? P.rowvec[gi] : INFINITY;      // the score of the row's ground-truth pair
       float st0 = (MODE == M_LSE || MODE == M_LSE2) ? -INFINITY : 0.f, st1 = 0.f;
       const int64_t my_diag_col = gi + P.diag_off;  // column index that is "the diagonal" of this row
@@ -345,7 +347,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (idx < 128) {
             const int64_t gj = (int64_t)jb * 128 + idx;
             float cv = INFINITY;
-            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * P.p0;
+            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * p0_eff;
             cbuf[b * 128 + idx] = cv;
           }
           ptx::named_bar_sync(1, kEpiThreads);
@@ -378,10 +380,10 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int c = 0; c < 32; ++c) cmax = fmaxf(cmax, __uint_as_float(v[c]));
             if (cmax != -INFINITY) {
-              const float mnew = fmaxf(st0, cmax * P.p0);
+              const float mnew = fmaxf(st0, cmax * p0_eff);
               float sum = 0.f;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) sum += scb_ex2(fmaf(__uint_as_float(v[c]), P.p0, -mnew));
+              for (int c = 0; c < 32; ++c) sum += scb_ex2(fmaf(__uint_as_float(v[c]), p0_eff, -mnew));
               st1 = st1 * scb_ex2(st0 - mnew) + sum;
               st0 = mnew;
             }
@@ -391,12 +393,12 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             float cmax = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 32; ++c) cmax = fmaxf(cmax, __uint_as_float(v[c]));
-            const float cm = cmax * P.p0;                       // -inf when every column of the chunk is dead
+            const float cm = cmax * p0_eff;                       // -inf when every column of the chunk is dead
             float ef[32];
             float sum = 0.f;
             const float cmf = (cmax != -INFINITY) ? cm : 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) { ef[c] = scb_ex2(fmaf(__uint_as_float(v[c]), P.p0, -cmf)); sum += ef[c]; }
+            for (int c = 0; c < 32; ++c) { ef[c] = scb_ex2(fmaf(__uint_as_float(v[c]), p0_eff, -cmf)); sum += ef[c]; }
             if (cmax != -INFINITY) {
               const float mnew = fmaxf(st0, cm);
               st1 = st1 * scb_ex2(st0 - mnew) + sum * scb_ex2(cm - mnew);
@@ -444,13 +446,13 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
                 const float g = __uint_as_float(v[c]);
-                const float y = g * P.p0;
+                const float y = g * p0_eff;
                 const float ww = scb_ex2(y - rowc) + scb_ex2(y - cb[c]);   // dead columns: 0 + 0
                 st0 = fmaf(ww, g, st0);
                 w[c] = ww;
               }
             } else {  // lunif: exp2(2 p0 g - p0 n_i - p0 n_j); dead columns carry +inf in cb -> 0
-              const float two_p0 = 2.f * P.p0;
+              const float two_p0 = 2.f * p0_eff;
 #pragma unroll
               for (int c = 0; c < 32; ++c) w[c] = scb_ex2(fmaf(__uint_as_float(v[c]), two_p0, -(rowc + cb[c])));
             }
@@ -665,37 +667,40 @@ int scb_tc_grad_kernel(int64_t nA, int D, int grad) {
   return (f & 2) ? 1 : 0;
 }
 int scb_tc_pair_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*,
-                            const float*, int64_t, int, float*, float*, cudaStream_t);
+                            const float*, int64_t, int, float*, float*, const float*, cudaStream_t);
 int scb_tc_pair_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
                       int64_t, int, float*, float*, float*, cudaStream_t);
 int scb_tc_quad_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*,
-                            const float*, int64_t, int, float*, float*, cudaStream_t);
+                            const float*, int64_t, int, float*, float*, const float*, cudaStream_t);
 int scb_tc_quad_lunif(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*, const float*,
                       int64_t, int, float*, float*, float*, cudaStream_t);
 
 int scb_tc_lse(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype, float scale,
-               int jparts, float* pm, float* pl, const int* run_flag, cudaStream_t s) {
+               int jparts, float* pm, float* pl, const int* run_flag, const float* scale_dev, cudaStream_t s) {
   TcParams P{};
+  P.p0_dev = scale_dev;
   P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.diag_off = INT64_MIN / 2; P.s0 = pm; P.s1 = pl; P.run_flag = run_flag;
   return launch_tc<M_LSE>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
 }
 // rows AND columns from one sweep: col_sum [4 n_rb][nB], col_ref [4 n_rb][ceil(nB/32)], n_rb = ceil(nA / 128)
 int scb_tc_lse2(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype, float scale,
-                int jparts, float* pm, float* pl, float* col_ref, float* col_sum, cudaStream_t s) {
+                int jparts, float* pm, float* pl, float* col_ref, float* col_sum, const float* scale_dev, cudaStream_t s) {
   TcParams P{};
+  P.p0_dev = scale_dev;
   P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.diag_off = INT64_MIN / 2; P.s0 = pm; P.s1 = pl; P.c0 = col_ref; P.c1 = col_sum;
   return launch_tc<M_LSE2>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);
 }
 int scb_tc_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                        float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts, float* out,
-                       float* ws, cudaStream_t s) {
+                       float* ws, const float* scale_dev, cudaStream_t s) {
   const int kern = scb_tc_grad_kernel(nA, D, 1);
   if (kern && (dtype == SCB_BF16 || dtype == SCB_F16) && D % 8 == 0 && ldA % 8 == 0 && ldB % 8 == 0 && scb_aligned16(A) &&
       scb_aligned16(Bm))
     return kern == 2
-               ? scb_tc_quad_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s)
-               : scb_tc_pair_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, s);
+               ? scb_tc_quad_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, scale_dev, s)
+               : scb_tc_pair_anchor_grad(A, nA, Bm, nB, D, ldA, ldB, dtype, scale, row_lse, col_lse, diag_off, jparts, out, ws, scale_dev, s);
   TcParams P{};
+  P.p0_dev = scale_dev;
   P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.rowvec = row_lse; P.colvec = col_lse; P.diag_off = diag_off;
   P.out = out; P.s0 = ws;
   return launch_tc<M_ANCHOR_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);

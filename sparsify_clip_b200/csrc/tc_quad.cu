@@ -61,6 +61,7 @@ struct QuadParams {
   int D, kch, n_rp, n_jb, jparts, nslots, fmt;
   int64_t span;                // tiles of the linearised (256-row block, column tile) space per cluster
   float p0;
+  const float* p0_dev;         // optional device multiplier of p0 (1/tau of a device-resident temperature)
   const float* rowvec;
   const float* colvec;
   int64_t diag_off;
@@ -230,6 +231,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 1)
 k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmBh, const QuadParams P) {
   extern __shared__ uint8_t smem_raw[];
+  const float p0_eff = P.p0_dev ? P.p0 * __ldg(P.p0_dev) : P.p0;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in every CTA
   const int kch = KCH ? KCH : P.kch;
   const int n_astat = KCH ? (KCH < kAStat ? KCH : kAStat) : min(kch, kAStat);
@@ -555,7 +557,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const bool row_ok = gi < P.nA;
       float rowc = 0.f;
       if (MODE == M_ANCHOR_GRAD) rowc = row_ok ? P.rowvec[gi] * SCB_LOG2E : 0.f;
-      if (MODE == M_LUNIF_GRAD) rowc = row_ok ? P.rowvec[gi] * P.p0 : 0.f;
+      if (MODE == M_LUNIF_GRAD) rowc = row_ok ? P.rowvec[gi] * p0_eff : 0.f;
       float st0 = 0.f, st1 = 0.f;
       const int64_t my_diag_col = gi + P.diag_off;
 
@@ -569,7 +571,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (idx < 128) {
             const int64_t gj = (int64_t)jb * 128 + idx;
             float cv = INFINITY;
-            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * P.p0;
+            if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * p0_eff;
             cbuf[b * 128 + idx] = cv;
           }
           ptx::named_bar_sync(1, kEpiThreads);
@@ -601,13 +603,13 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
             for (int cx = 0; cx < 32; ++cx) {
               const float gg = __uint_as_float(v[cx]);
-              const float y = gg * P.p0;
+              const float y = gg * p0_eff;
               const float ww = scb_ex2(y - rowc) + scb_ex2(y - cb[cx]);   // dead columns: 0 + 0
               st0 = fmaf(ww, gg, st0);
               w[cx] = ww;
             }
           } else {  // lunif: exp2(2 p0 g - p0 n_i - p0 n_j); dead columns carry +inf in cb -> 0
-            const float two_p0 = 2.f * P.p0;
+            const float two_p0 = 2.f * p0_eff;
 #pragma unroll
             for (int cx = 0; cx < 32; ++cx) w[cx] = scb_ex2(fmaf(__uint_as_float(v[cx]), two_p0, -(rowc + cb[cx])));
           }
@@ -758,8 +760,8 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }  // namespace
 
 int scb_tc_pair_range(int mode, const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
-                      float p0, const float* rowvec, const float* colvec, int64_t diag_off, int jparts, int64_t slot_rows,
-                      float* out, float* s0, float* s1, int max_pairs, cudaStream_t s);
+                      float p0, const float* p0_dev, const float* rowvec, const float* colvec, int64_t diag_off, int jparts,
+                      int64_t slot_rows, float* out, float* s0, float* s1, int max_pairs, cudaStream_t s);
 
 unsigned long long* scb_pair_trace_buffer();   // tc_pair.cu (null unless built with -DSCB_PAIR_TRACE and armed)
 int scb_make_tmap_2d_box(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype, int box_rows);   // tc_pass.cu
@@ -968,7 +970,7 @@ int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
   const char* A2 = static_cast<const char*>(A) + (size_t)r0 * (size_t)ldA * 2u;
   int rc2 = 0;
   if (rc == 0)
-    rc2 = scb_tc_pair_range(MODE, A2, nA - r0, Bm, nB, D, ldA, ldB, dtype, P.p0, P.rowvec + r0, P.colvec, P.diag_off + r0, P.jparts, nA,
+    rc2 = scb_tc_pair_range(MODE, A2, nA - r0, Bm, nB, D, ldA, ldB, dtype, P.p0, P.p0_dev, P.rowvec + r0, P.colvec, P.diag_off + r0, P.jparts, nA,
                             P.out + (size_t)r0 * D, P.s0 ? P.s0 + r0 : nullptr, P.s1 ? P.s1 + r0 : nullptr, q.side_pairs, s);
   // always join, also after a failed launch: the caller's stream must not be left without the dependency
   e = cudaEventRecord(side->join, side->hi);
@@ -983,8 +985,9 @@ int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, in
 
 int scb_tc_quad_anchor_grad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                             float scale, const float* row_lse, const float* col_lse, int64_t diag_off, int jparts,
-                            float* out, float* ws, cudaStream_t s) {
+                            float* out, float* ws, const float* scale_dev, cudaStream_t s) {
   QuadParams P{};
+  P.p0_dev = scale_dev;
   P.jparts = jparts; P.p0 = scale * SCB_LOG2E; P.rowvec = row_lse; P.colvec = col_lse; P.diag_off = diag_off;
   P.out = out; P.s0 = ws;
   return launch_quad<M_ANCHOR_GRAD>(A, nA, Bm, nB, D, ldA, ldB, dtype, P, s);

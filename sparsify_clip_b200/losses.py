@@ -99,6 +99,15 @@ def _common(a, b):
     return a, b
 
 
+def _scale_of(tau_t, tau_f):
+    """-> (host scale, device multiplier or None).  A float or a CPU tensor (the reference's placement,
+    sparsify_clip.py:716-717) gives the host float 1/tau.  A CUDA tensor is NOT read on the host: the kernels get scale = 1
+    and a one-element device tensor 1/tau (no synchronisation; a captured CUDA graph follows the parameter)."""
+    if tau_t is not None and tau_t.is_cuda:
+        return 1.0, (1.0 / tau_t.detach().to(torch.float32)).reshape(1)
+    return 1.0 / (float(tau_t) if tau_t is not None else float(tau_f)), None
+
+
 def _gout32(g):
     return g.detach().to(torch.float32).reshape(()).contiguous()
 
@@ -114,21 +123,22 @@ class _AnchorFn(torch.autograd.Function):
         be = get_backend()
         I, T = _common(I, T)
         Ip, Tp = be.prep(I), be.prep(T)
-        tau = float(tau_t) if tau_t is not None else float(tau_f)
-        scale = 1.0 / tau
+        scale, sdev = _scale_of(tau_t, tau_f)
         rank, ws = _world(group)
         n = Ip.shape[0]
         I_all, T_all = _all_gather_rows(Ip, group), _all_gather_rows(Tp, group)
         if group is None:
-            r, c = be.lse_rows_cols(Ip, Tp, scale)    # row and column LSE from one sweep over S
+            r, c = be.lse_rows_cols(Ip, Tp, scale, scale_dev=sdev)    # row and column LSE from one sweep over S
         else:
-            r = be.lse(Ip, T_all, scale)              # row LSE of the local rows of S
-            c = be.lse(Tp, I_all, scale)              # column LSE of the local columns of S
+            r = be.lse(Ip, T_all, scale, scale_dev=sdev)              # row LSE of the local rows of S
+            c = be.lse(Tp, I_all, scale, scale_dev=sdev)              # column LSE of the local columns of S
         diag = be.row_dot(Ip, Tp)
-        part = be.sum(r) + be.sum(c) - (2.0 * scale) * be.sum(diag)
+        sfac = scale if sdev is None else sdev[0]
+        part = be.sum(r) + be.sum(c) - (2.0 * sfac) * be.sum(diag)
         _all_reduce_(part, group)
         B = n * ws
         ctx.group, ctx.scale, ctx.B, ctx.off = group, scale, B, rank * n
+        ctx.sdev = sdev
         ctx.in_dtypes = (I.dtype, T.dtype)
         ctx.tau_meta = None if tau_t is None else (tau_t.dtype, tau_t.device, tau_t.shape)
         ctx.save_for_backward(Ip, Tp, I_all, T_all, r, c, diag)
@@ -143,20 +153,22 @@ class _AnchorFn(torch.autograd.Function):
         need_I, need_T, need_tau = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         r_all, c_all = _all_gather_rows(r, group), _all_gather_rows(c, group)
         coef = scale / (2.0 * B)
+        sdev = ctx.sdev
         dI = dT = dtau = None
         ws_sum = None
         if need_I or need_tau:
-            dI, ws_sum = be.anchor_grad(Ip, T_all, Tp, scale, r, c_all, c, diag, off, coef, g, need_tau)
+            dI, ws_sum = be.anchor_grad(Ip, T_all, Tp, scale, r, c_all, c, diag, off, coef, g, need_tau, scale_dev=sdev)
             dI = dI.to(ctx.in_dtypes[0]) if need_I else None
         if need_T:
-            dT, _ = be.anchor_grad(Tp, I_all, Ip, scale, c, r_all, r, diag, off, coef, g, False)
+            dT, _ = be.anchor_grad(Tp, I_all, Ip, scale, c, r_all, r, diag, off, coef, g, False, scale_dev=sdev)
             dT = dT.to(ctx.in_dtypes[1])
         if need_tau:
             # d/dtau = -(1/tau) sum_ij G_ij S_ij,  G = (P + Q - 2 I_B)/(2B),  S = scale * (a.b)
             part = ws_sum - 2.0 * be.sum(diag)
             _all_reduce_(part, group)
             dt, dev, shp = ctx.tau_meta
-            dtau = (part * g * (-(scale * scale) / (2.0 * B))).to(device=dev, dtype=dt).reshape(shp)
+            s2 = scale * scale if sdev is None else sdev[0] * sdev[0]
+            dtau = (part * g * (-s2 / (2.0 * B))).to(device=dev, dtype=dt).reshape(shp)
         return dI, dT, dtau, None, None
 
 
@@ -303,20 +315,19 @@ class _FusedTermsFn(torch.autograd.Function):
         hI = _await(hI)
         _unif(w_i, Ip, I_all, need_I, "I", 4)
         an_I = an_T = None
-        scale = 0.0
+        scale, sdev = 0.0, None
         r = c = None
         colparts = None
         if w_a != 0.0:
             hT = _await(hT)
-            tau = float(tau_t) if tau_t is not None else float(tau_f)
-            scale = 1.0 / tau
+            scale, sdev = _scale_of(tau_t, tau_f)
             if group is None:
-                r, c = be.lse_rows_cols(Ip, Tp, scale)      # both from one sweep over S
+                r, c = be.lse_rows_cols(Ip, Tp, scale, scale_dev=sdev)      # both from one sweep over S
             else:
-                colparts = be.lse_rows_colparts(Ip, T_all, Tp, I_all, scale)
+                colparts = be.lse_rows_colparts(Ip, T_all, Tp, I_all, scale, scale_dev=sdev)
                 if colparts is None:                        # not on the tensor-core path: two sweeps
-                    r = be.lse(Ip, T_all, scale)
-                    c = be.lse(Tp, I_all, scale)
+                    r = be.lse(Ip, T_all, scale, scale_dev=sdev)
+                    c = be.lse(Tp, I_all, scale, scale_dev=sdev)
                 else:                                       # one sweep: my rows of S; the column sums are folded
                     r = colparts[0]                         # over the ranks after the gather below
             diag = be.row_dot(Ip, Tp)
@@ -367,15 +378,17 @@ class _FusedTermsFn(torch.autograd.Function):
             if group is not None and (not gathered or w_t != 0.0 or w_c != 0.0):
                 hR = _SmallReduce(parts[late_lo:NS].clone(), group, "R")      # reduced under the anchor-gradient sweeps
             if need_I or need_tau:
-                p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau)
-                an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef)
+                p = be.anchor_grad_pass(Ip, T_all, scale, r, c_all, off, need_tau, scale_dev=sdev)
+                an_I = dict(out=p["out"], jparts=p["jparts"], row_lse=r, col_lse_rows=c, diag=diag, scale=scale, coef=coef,
+                            scale_dev=sdev)
                 if need_tau:
                     parts[NS] = p["ws"] - 2.0 * local_sdiag
                     if group is not None:                    # reduced under the dT sweep
                         hD = _SmallReduce(parts[NS:].clone(), group, "D")
             if need_T:
-                p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False)
-                an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef)
+                p = be.anchor_grad_pass(Tp, I_all, scale, c, r_all, off, False, scale_dev=sdev)
+                an_T = dict(out=p["out"], jparts=p["jparts"], row_lse=c, col_lse_rows=r, diag=diag, scale=scale, coef=coef,
+                            scale_dev=sdev)
             if hR is not None:
                 parts[late_lo:NS] = hR.result()
             if hD is not None:
@@ -384,7 +397,8 @@ class _FusedTermsFn(torch.autograd.Function):
             from . import peer
             peer.release_all()          # every sweep that reads a gathered buffer is enqueued: the peers may refill them
         # the additions of the ladder on the (now global) partial sums, and 1 / Ssum of every L_unif term, in one launch
-        loss, inv_ssum = be.loss_assemble(parts, w_a / (2.0 * B), 2.0 * scale, w_l / B, w_i, w_t, w_c, B * (B - 1) / 2.0)
+        loss, inv_ssum = be.loss_assemble(parts, w_a / (2.0 * B), 2.0 * scale, w_l / B, w_i, w_t, w_c, B * (B - 1) / 2.0,
+                                          scale_dev=sdev)
         cen = un_I = un_T = None
         for which, (core, wu, needx, k) in cores.items():
             if needx:
@@ -401,7 +415,8 @@ class _FusedTermsFn(torch.autograd.Function):
         dtau = None
         if need_tau and w_a != 0.0:
             dt, tdev, shp = tau_t.dtype, tau_t.device, tau_t.shape
-            dtau = (parts[NS] * (-(w_a * scale * scale) / (2.0 * B))).to(device=tdev, dtype=dt).reshape(shp)
+            s2 = scale * scale if sdev is None else sdev[0] * sdev[0]
+            dtau = (parts[NS] * (s2 * (-w_a / (2.0 * B)))).to(device=tdev, dtype=dt).reshape(shp)
         # The per-operand combine runs in backward with grad_output as its device-side scale: one pass writes the final
         # gradient in the input dtype (no separate multiply).  The sweep outputs stay alive until then.
         okdt = (torch.float32, torch.bfloat16, torch.float16)

@@ -25,7 +25,7 @@ class FakeBackend:
             return out
         return v
 
-    def loss_assemble(self, parts, c_anchor, two_scale, c_align, w_img, w_txt, w_cen, pair_norm):
+    def loss_assemble(self, parts, c_anchor, two_scale, c_align, w_img, w_txt, w_cen, pair_norm, scale_dev=None):
         p = parts.double()
         loss = torch.zeros((), dtype=torch.float64)
         if c_anchor != 0.0:
@@ -81,14 +81,14 @@ class FakeBackend:
         Mx = Mr.max(0).values
         return (Mx + torch.log2((Lr * torch.exp2(Mr - Mx)).sum(0))) * math.log(2.0)
 
-    def lse(self, A, Ball, scale):
+    def lse(self, A, Ball, scale, scale_dev=None):
         return torch.logsumexp(scale * A @ Ball.t(), dim=1)
 
-    def lse_rows_cols(self, A, Bm, scale):
+    def lse_rows_cols(self, A, Bm, scale, scale_dev=None):
         S = scale * A @ Bm.t()
         return torch.logsumexp(S, dim=1), torch.logsumexp(S, dim=0)
 
-    def lse_rows_colparts(self, A, Bm_all, Bm_rows, A_all, scale):
+    def lse_rows_colparts(self, A, Bm_all, Bm_rows, A_all, scale, scale_dev=None):
         S = (scale * A @ Bm_all.t()) / 0.6931471805599453        # log2 domain, as the kernels
         M = S.max(0).values
         L = torch.exp2(S - M).sum(0)
@@ -96,7 +96,7 @@ class FakeBackend:
         return r, M, L, torch.zeros(Bm_rows.shape[0], dtype=A.dtype), torch.zeros(1, dtype=torch.int32)
 
     def anchor_grad(self, A, Ball, V_rows, scale, row_lse, col_lse_all, col_lse_rows, diag, diag_off, host_scale,
-                    dev_scale, want_ws):
+                    dev_scale, want_ws, scale_dev=None):
         G0 = A @ Ball.t()
         S = scale * G0
         W = torch.exp(S - row_lse[:, None]) + torch.exp(S - col_lse_all[None, :])
@@ -109,7 +109,7 @@ class FakeBackend:
         dA = host_scale * dev_scale.double() * (Wd @ Ball + dcoef[:, None] * V_rows)
         return dA, ws
 
-    def anchor_grad_pass(self, A, Ball, scale, row_lse, col_lse_all, diag_off, want_ws):
+    def anchor_grad_pass(self, A, Ball, scale, row_lse, col_lse_all, diag_off, want_ws, scale_dev=None):
         G0 = A @ Ball.t()
         S = scale * G0
         W = torch.exp(S - row_lse[:, None]) + torch.exp(S - col_lse_all[None, :])

@@ -137,3 +137,49 @@ def test_train_step_on_gpu_matches_eager_reference_arithmetic(amp):
         assert abs(got.item() - want.item()) <= tol * max(1.0, abs(want.item())), (amp, epoch, got.item(), want.item())
         assert all(torch.isfinite(p).all() for p in model.parameters())
         assert ts.temperature.grad is None or torch.isfinite(ts.temperature.grad).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("epoch", [0, 1])
+def test_train_step_parameter_gradients_match_the_eager_reference_chain(epoch):
+    """One c5 step, fp32: the gradient that reaches EVERY encoder parameter (through pre-loss normalise -> loss ladder,
+    sparsify_clip.py:768-938) and the learnable temperature, against the reference's op sequence in eager PyTorch
+    autograd on an identical copy of the towers."""
+    import copy
+
+    import torch.nn.functional as F
+    cfg = dict(CFG, fp16=False, anchor_temperature_learnable=True)
+    images, tokens = _data(96, 7)
+    images, tokens = images.cuda(), tokens.cuda()
+    torch.manual_seed(0)
+    model = MiniCLIP(**TINY).cuda()
+    ref_model = copy.deepcopy(model)
+    ts = TrainStep(model, cfg, t_total=10, amp_dtype=None, steps_sparsify=0)
+    img, txt = ts.embed(images, tokens)
+    loss = ts.loss(img, txt, epoch)
+    (loss * 7.0).backward()
+    # the reference's own lines: :768-773 encode + normalise, :796-809 the exp-6 ladder
+    tau = torch.nn.Parameter(torch.tensor(0.1))
+    i, t = ref_model.encode_image(images), ref_model.encode_text(tokens)
+    i = i / i.norm(dim=-1, keepdim=True)
+    t = t / t.norm(dim=-1, keepdim=True)
+    lunif = lambda x: torch.pdist(x, p=2).pow(2).mul(-2).exp().mean().log()
+    if epoch == 0:
+        want = (lunif(i) + lunif(t)) / 2
+    else:
+        logits = i @ t.t() / tau
+        tgt = torch.arange(96, device="cuda")
+        want = ((F.cross_entropy(logits, tgt) + F.cross_entropy(logits.t(), tgt)) / 2 + (i - t).norm(dim=1).pow(2).mean()
+                + lunif(F.normalize((i + t) / 2, dim=-1)))
+    (want * 7.0).backward()
+    assert abs(loss.item() - want.item()) <= 1e-5 * max(1.0, abs(want.item()))
+    num = den = 0.0
+    for (name, p), q in zip(model.named_parameters(), ref_model.parameters()):
+        if q.grad is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, name
+            continue
+        num += (p.grad.double() - q.grad.double()).pow(2).sum().item()
+        den += q.grad.double().pow(2).sum().item()
+    assert math.sqrt(num / den) <= 2e-4, math.sqrt(num / den)      # fp32 encoders: the two chains differ by fp32 rounding only
+    if epoch == 1:
+        assert ts.temperature.grad.item() == pytest.approx(tau.grad.item(), rel=1e-4)

@@ -163,3 +163,52 @@ def test_random_alignment_loss_draws_from_the_cpu_generator_like_the_reference()
     idx = torch.randperm(256)
     b = cf.lalign_loss(I.float().cpu().numpy(), T.float().cpu().numpy()[idx.numpy()], need_grad=False)
     assert a == pytest.approx(b, rel=1e-5)
+
+
+@pytest.mark.parametrize("B,D,dtype", [(384, 512, torch.bfloat16), (1000, 768, torch.bfloat16), (200, 96, torch.float32)])
+def test_device_resident_temperature(B, D, dtype):
+    """The temperature as a CUDA parameter (SURVEY.md §8b allows it next to the reference's CPU parameter,
+    sparsify_clip.py:716-717): the kernels read 1/tau on the device (scale_dev).  Same loss, gradients and d/dtau as with
+    the host float; d/dtau comes back on the GPU; a CUDA graph captured once follows the parameter when it changes."""
+    g = torch.Generator(device="cuda").manual_seed(B)
+    I0 = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device="cuda"), dim=-1).to(dtype)
+    T0 = torch.nn.functional.normalize(I0.float() + 0.5 * torch.randn(B, D, generator=g, device="cuda"), dim=-1).to(dtype)
+    w = dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0)
+    ref, dI, dT, dtau, terms = cf.weighted_loss(I0.double().cpu().numpy(), T0.double().cpu().numpy(), 0.1, 1.0, 1.0, 0.5, 0.5, 0.0)
+    gtol = 1e-5 if dtype == torch.float32 else 6e-3
+    for fused in (True, False):
+        prev = scb.set_fused(fused)
+        try:
+            I, T = I0.clone().requires_grad_(True), T0.clone().requires_grad_(True)
+            tau = torch.nn.Parameter(torch.tensor(0.1, device="cuda"))
+            loss = scb.weighted_loss(I, T, tau, w)
+            loss.backward()
+        finally:
+            scb.set_fused(prev)
+        assert abs(loss.item() - ref) <= 1e-5 * sum(abs(v) for v in terms.values())
+        assert tau.grad.is_cuda and abs(tau.grad.item() - dtau) <= max(1e-3 if dtype != torch.float32 else 1e-5, 0) * abs(dtau)
+        assert np.linalg.norm(I.grad.double().cpu().numpy() - dI) <= gtol * np.linalg.norm(dI)
+        assert np.linalg.norm(T.grad.double().cpu().numpy() - dT) <= gtol * np.linalg.norm(dT)
+    # graph replay follows the parameter
+    I, T = I0.clone().requires_grad_(True), T0.clone().requires_grad_(True)
+    tau = torch.nn.Parameter(torch.tensor(0.1, device="cuda"))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        scb.weighted_loss(I, T, tau, w).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    I.grad = T.grad = tau.grad = None
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        gl = scb.weighted_loss(I, T, tau, w)
+        gl.backward()
+    gr.replay()
+    torch.cuda.synchronize()
+    assert abs(gl.item() - ref) <= 1e-5 * sum(abs(v) for v in terms.values())
+    with torch.no_grad():
+        tau.fill_(0.25)
+    gr.replay()
+    torch.cuda.synchronize()
+    ref2, _, _, dtau2, terms2 = cf.weighted_loss(I0.double().cpu().numpy(), T0.double().cpu().numpy(), 0.25, 1.0, 1.0, 0.5, 0.5, 0.0)
+    assert abs(gl.item() - ref2) <= 1e-5 * sum(abs(v) for v in terms2.values())
+    assert abs(tau.grad.item() - dtau2) <= (1e-3 if dtype != torch.float32 else 1e-5) * abs(dtau2)

@@ -73,7 +73,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     lib = _lib.load()
     rc = lib.scb_row_sqnorm(None, 4, 8, 8, 7, None, None)       # bad dtype
     assert rc == -2 and b"dtype" in lib.scb_last_error()
-    rc = lib.scb_lse_pass(None, 4, None, 4, 8, 8, 8, _lib.SCB_BF16, 1.0, 0, None, None, _lib.PATH_TC, None)
+    rc = lib.scb_lse_pass(None, 4, None, 4, 8, 8, 8, _lib.SCB_BF16, 1.0, 0, None, None, _lib.PATH_TC, None, None)
     assert rc == -1
     with pytest.raises(ValueError):
         _lib.check(rc, "lse_pass")
@@ -85,13 +85,13 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert b"offsets" in lib.scb_last_error()
     assert lib.scb_lse2_fold_ranks(p, 0, 100, 10, 10, 25, 45, f, p, None) == -1      # world = 0
     assert lib.scb_lse2_fold_ranks(p, 2, 100, 0, 0, 0, 0, f, p, None) == 0           # nothing to do
-    assert lib.scb_loss_assemble(None, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, p, p, None) == -1
+    assert lib.scb_loss_assemble(None, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, p, p, None, None) == -1
     # the fused combine: a term's inputs must come together, the output layout must hold a row
     assert lib.scb_grad_combine(p, None, 4, 8, 8, 8, _lib.SCB_BF16, p, 1, None, None, None, 1.0, 1.0, None, 0, None, 0, 0.0,
-                                None, 0.0, None, 0.0, None, p, _lib.SCB_BF16, 8, None) == -1
+                                None, 0.0, None, 0.0, None, p, _lib.SCB_BF16, 8, None, None) == -1
     assert b"anchor" in lib.scb_last_error()
     assert lib.scb_grad_combine(p, p, 4, 8, 8, 8, _lib.SCB_BF16, None, 0, None, None, None, 1.0, 1.0, None, 0, None, 0, 0.0,
-                                None, 1.0, None, 0.0, None, p, _lib.SCB_BF16, 4, None) == -1
+                                None, 1.0, None, 0.0, None, p, _lib.SCB_BF16, 4, None, None) == -1
 
 
 def test_no_cpu_fallback():
