@@ -269,6 +269,8 @@ int scb_peer_push(const void* src, int64_t bytes, void* const* dst, int n, const
 int scb_peer_copy(const void* src, int64_t bytes, void* const* dst, int n, void* stream);
 int scb_peer_wait(const int* epoch, const int* arrived, int world, void* stream);
 int scb_peer_release(const int* epoch, int* const* done_words, int world, void* stream);
+/* the same for up to 8 roles in one launch (host arrays of the per-role arguments) */
+int scb_peer_release_many(const int* const* epochs, int* const* const* done_words, int n_roles, int world, void* stream);
 
 /* debug: device buffer of 2 x 4 x 4096 x 2 uint64 that the CTA-pair kernel fills with a per-role timeline of
  * cluster 0 (tag, tile, clock64) on the following launches; NULL switches it off (tools/pair_trace.py). */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "scb_peer_copy": [_vp, _i64, ctypes.POINTER(ctypes.c_void_p), _i32, _vp],
     "scb_peer_wait": [_vp, _vp, _i32, _vp],
     "scb_peer_release": [_vp, _vp, _i32, _vp],
+    "scb_peer_release_many": [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p), _i32, _i32, _vp],
     "scb_rank_count_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _vp],
 }
 

@@ -272,6 +272,18 @@ __global__ void k_peer_wait(const int* __restrict__ epoch, const volatile int* _
   if ((int)threadIdx.x < world) spin_until_ge(arrived + threadIdx.x, *epoch);
   __threadfence_system();
 }
+struct ReleaseMany {
+  const int* epoch[8];
+  int* const* words[8];
+};
+// several roles released by one launch: warp r handles role r
+__global__ void k_peer_release_many(const ReleaseMany a, int world) {
+  const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < world) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(a.words[r][lane]) = *a.epoch[r];
+  }
+}
 }  // namespace
 
 extern "C" int scb_peer_alloc(int64_t bytes, void** ptr, unsigned char* handle64) {
@@ -345,5 +357,17 @@ extern "C" int scb_peer_release(const int* epoch, int* const* done_words, int wo
   SCB_CHECK_ARG(epoch && done_words && world >= 1 && world <= 32, SCB_E_ARG, "peer_release: bad argument");
   k_peer_signal<<<1, 32, 0, (cudaStream_t)stream>>>(epoch, done_words, world);
   SCB_CHECK_LAUNCH("peer_release");
+  return 0;
+}
+
+// scb_peer_release for up to 8 roles in one launch (epochs[r], done_words[r] as for scb_peer_release)
+extern "C" int scb_peer_release_many(const int* const* epochs, int* const* const* done_words, int n_roles, int world,
+                                     void* stream) {
+  SCB_CHECK_ARG(epochs && done_words && n_roles >= 1 && n_roles <= 8 && world >= 1 && world <= 32, SCB_E_ARG,
+                "peer_release_many: bad argument");
+  ReleaseMany a{};
+  for (int r = 0; r < n_roles; ++r) { a.epoch[r] = epochs[r]; a.words[r] = done_words[r]; }
+  k_peer_release_many<<<1, 32 * n_roles, 0, (cudaStream_t)stream>>>(a, world);
+  SCB_CHECK_LAUNCH("peer_release_many");
   return 0;
 }

@@ -144,11 +144,23 @@ class PeerGather:
 
 
 def release_all():
-    """After the last read of every gathered buffer of this step (stream-ordered): let the peers overwrite them."""
-    for pg in _state["open"]:
-        if pg.open_reads:
-            pg.release()
+    """After the last read of every gathered buffer of this step (stream-ordered): let the peers overwrite them.
+    One launch for all roles of a device (the flag kernels are tiny, but at 8 GPUs a step is only ~1.2 ms)."""
+    todo = [pg for pg in _state["open"] if pg.open_reads]
     _state["open"].clear()
+    while todo:
+        dev = todo[0].device
+        batch = [pg for pg in todo if pg.device == dev and pg.world == todo[0].world][:8]
+        todo = [pg for pg in todo if pg not in batch]
+        cur = torch.cuda.current_stream(dev)
+        for pg in batch:
+            cur.wait_stream(pg.stream)         # joins the side streams (required inside a graph capture)
+        n = len(batch)
+        ep = (ctypes.c_void_p * n)(*[pg.epoch.data_ptr() for pg in batch])
+        dw = (ctypes.c_void_p * n)(*[pg.done_words.data_ptr() for pg in batch])
+        check(batch[0].lib.scb_peer_release_many(ep, dw, n, batch[0].world, cur.cuda_stream), "peer_release_many")
+        for pg in batch:
+            pg.open_reads = False
 
 
 def available(group, device):
