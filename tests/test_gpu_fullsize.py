@@ -32,8 +32,10 @@ def _synth(B, D, seed=42):
 
 def _sample_rows(B, n=64, seed=1):
     g = torch.Generator().manual_seed(seed)
-    rows = torch.randperm(B, generator=g)[:n - 4]
-    return torch.cat([rows, torch.tensor([0, 127, 128, B - 1])]).unique().cuda()
+    rows = torch.randperm(B, generator=g)[:n - 8]
+    # fixed extras: tile edges and the neighbourhood of the row split (the last ~6 % of the rows run on the CTA-pair kernel)
+    extra = [0, 127, 128, B - 1, int(0.93 * B), int(0.95 * B), max(0, B - 130), max(0, B - 700)]
+    return torch.cat([rows, torch.tensor(extra)]).unique().cuda()
 
 
 def _check_config(B, D, tau, w, learnable_tau, slab):
@@ -97,6 +99,12 @@ def test_c4_shard_exp10_vs_chunked_fp64_oracle():
 def test_c2_exp4_vs_chunked_fp64_oracle():
     """BASELINE c2: exp 4 (anchor + lalign + lunif(centroids)), B = 4096, D = 512."""
     _check_config(4096, 512, 0.1, dict(anchor=1.0, align=1.0, unif_img=0.0, unif_txt=0.0, unif_cen=1.0), False, 4096)
+
+
+def test_odd_row_block_count_exp3_vs_chunked_fp64_oracle():
+    """B = 10000 (79 row blocks: the clusters of 4 get an odd number of them and a half-empty last 256-row block, the
+    CTA-pair side kernel the last 4), D = 512, tau = 0.07."""
+    _check_config(10000, 512, 0.07, dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0), True, 2048)
 
 
 def test_d1024_exp3_vs_chunked_fp64_oracle():

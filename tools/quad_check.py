@@ -39,7 +39,7 @@ print("grad kernel kind at nA=384, D=512:", be.lib.scb_grad_kernel_kind(384, 512
 QF = int(os.environ.get("QUAD_FLAGS", "15"))
 ok = True
 sizes = [(256, 512, 0.1), (384, 512, 0.1), (129, 264, 0.1), (640, 320, 0.1), (385, 384, 0.07), (1300, 448, 0.1), (2100, 456, 0.05),
-         (1024, 512, 0.1), (5000, 512, 0.1), (8192, 512, 0.1), (12000, 448, 0.1)]
+         (1024, 512, 0.1), (5000, 512, 0.1), (8192, 512, 0.1), (12000, 448, 0.1), (10000, 512, 0.07), (8960, 384, 0.1)]
 if len(sys.argv) > 1 and sys.argv[1] == "first":
     sizes = sizes[:2]
 for (B, D, tau) in sizes:
