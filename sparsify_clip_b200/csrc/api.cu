@@ -28,7 +28,7 @@ int scb_quad_clusters();
 void scb_pair_span_plan(int64_t n_rb, int64_t n_jb, int n_sm, int* n_pairs, int64_t* span, int* pmax);
 void scb_quad_span_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int* n_used, int64_t* span, int* pmax);
 struct QuadSplit { int64_t rows_quad; int side_pairs; int jparts; };
-QuadSplit scb_quad_split(int64_t nA, int64_t nB, int n_sm);
+QuadSplit scb_quad_split(int64_t nA, int64_t nB, int D, int n_sm);
 
 #define SCB_PASS_CHECKS(A, nA, Bm, nB, D, ldA, ldB, dtype, jparts, path)                                           \
   SCB_CHECK_ARG(scb_dtype_ok(dtype), SCB_E_DTYPE, "%s: unsupported dtype %d", __func__, (int)(dtype));             \
@@ -62,7 +62,7 @@ extern "C" int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, 
     const int64_t n_rb = (nA + 127) / 128, n_jb = (nB + 127) / 128;
     const int kern = n_sm >= 2 ? scb_tc_grad_kernel(nA, D, grad) : 0;
     if (kern == 2) {            // equal contiguous spans of (256-row block, tile) per cluster of 4 (tc_quad.cu), the last
-      *jparts = scb_quad_split(nA, nB, n_sm).jparts;      // rows on CTA pairs; cluster count = a property of the device
+      *jparts = scb_quad_split(nA, nB, D, n_sm).jparts;      // rows on CTA pairs; cluster count = a property of the device
       *nsub = 4;
     } else if (kern == 1) {     // equal contiguous spans of (row block, tile) per CTA pair
       int np = 0;

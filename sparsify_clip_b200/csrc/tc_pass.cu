@@ -662,9 +662,9 @@ int scb_make_tmap_2d_box(CUtensorMap* m, const void* base, int64_t rows, int D, 
 int scb_tc_grad_kernel(int64_t nA, int D, int grad) {
   const int kch = (D + 63) / 64;
   const int f = g_tc_flags.load();
-  if (!grad || kch <= 4 || kch > 8) return 0;
-  if ((f & 4) && nA > 128 && scb_quad_clusters() > 0) return 2;
-  return (f & 2) ? 1 : 0;
+  if (!grad || kch <= 4 || kch > 16) return 0;
+  if ((f & 4) && nA > 128 && scb_quad_clusters() > 0) return 2;     // clusters of 4: 256 < D <= 1024 (column groups)
+  return ((f & 2) && kch <= 8) ? 1 : 0;                              // CTA pairs: 256 < D <= 512
 }
 int scb_tc_pair_anchor_grad(const void*, int64_t, const void*, int64_t, int, int64_t, int64_t, int, float, const float*,
                             const float*, int64_t, int, float*, float*, const float*, cudaStream_t);

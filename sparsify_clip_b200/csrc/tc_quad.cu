@@ -1,4 +1,6 @@
-// tc_quad.cu -- gradient passes on a CLUSTER OF FOUR CTAs (two cta_group::2 pairs, sm_100a) for 256 < D <= 512.
+// tc_quad.cu -- gradient passes on a CLUSTER OF FOUR CTAs (two cta_group::2 pairs, sm_100a) for 256 < D <= 1024.
+// (D > 512: the output columns are covered by successive launches, "column groups" of up to 8 K-chunks, each of which
+// recomputes the S tiles over the full D -- see launch_quad_rows.)
 //
 // k_tc_pair (tc_pair.cu) is bound by shared-memory bandwidth, not by the tensor pipe: its MMA1 is a single-CTA
 // M128.N128.K16 SS instruction that reads 8 KB of operands per 64 cycles -- all of an SM's 128 B/clk -- and every
@@ -59,6 +61,9 @@ struct QuadParams {
   int64_t nA, nB;
   int64_t slot_rows;           // rows of one output partial slot (= rows of the whole pass; this launch may cover a row range)
   int D, kch, n_rp, n_jb, jparts, nslots, fmt;
+  int ch0, cpc;                // column group of this launch: output chunks (64 columns) [ch0, ch0 + 4 cpc); CTA (h, c) of a
+                               // cluster owns chunks ch0 + 2 cpc h + cpc c + {0 .. cpc-1}; cpc = 2 (MMA2 N = 256) or 1 (N = 128).
+                               // The row statistics do not depend on the group: only the launch with ch0 == 0 writes them
   int64_t span;                // tiles of the linearised (256-row block, column tile) space per cluster
   float p0;
   const float* p0_dev;         // optional device multiplier of p0 (1/tau of a device-resident temperature)
@@ -350,7 +355,8 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // valid chunk and never stored)
       auto load_v = [&](int tt, int tag) {
         for (int u = 0; u < 2; ++u) {
-          int ch = 4 * (int)h + 2 * (int)c + u;
+          if (u >= P.cpc) { (void)slot_begin(0u, tag); continue; }    // one chunk per CTA: the pair's second slot stays empty
+          int ch = P.ch0 + P.cpc * (2 * (int)h + (int)c) + u;
           if (ch >= kch) ch = kch - 1;
           load_full(&tmB, ch * 64, (jb_lo + tt) * 128, tag);
         }
@@ -387,7 +393,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t a_full_par = 0, out_empty_par = 1, item_cnt = 0;
       uint32_t k1 = 0, k2 = 0, kp = 0;   // issued MMA1 (own tiles), MMA2 on own tiles, MMA2 on the other pair's tiles
       const uint32_t idesc1 = ptx::idesc_f16(256, 128, P.fmt, P.fmt, 0, 0);
-      const uint32_t idesc2 = ptx::idesc_f16(256, 256, P.fmt, P.fmt, 0, 1);
+      const uint32_t idesc2 = ptx::idesc_f16(256, 128 * P.cpc, P.fmt, P.fmt, 0, 1);
       const uint32_t a_lo0 = ptx::desc_lo(sm_a, 16);
       const uint32_t w_lo0 = ptx::desc_lo(sm_w, 16);
       const uint32_t ring_lo0 = ptx::desc_lo(sm_ring, 16);
@@ -645,17 +651,19 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }  // own tiles
 
-      // ---- drain my quarter of the output accumulator (my 128 rows x my pair's 256 columns)
+      // ---- drain my quarter of the output accumulator (my 128 rows x my pair's 128 cpc columns)
+      const int ow = 64 * P.cpc;                                // output columns this warp drains
+      const int pair_col0 = 64 * (P.ch0 + 2 * P.cpc * (int)h);  // first output column of my pair in this column group
       if (nt > 0) {
         ptx::mbar_wait(bar(BAR_OUT_FULL), item_cnt & 1u, 320);
         ptx::tc_fence_after();
         float* orow = P.out + ((int64_t)jp * P.slot_rows + gi) * P.D;
-        for (int c0 = 0; c0 < 128; c0 += 32) {
+        for (int c0 = 0; c0 < ow; c0 += 32) {
           uint32_t v[32];
-          const int ocol = hh * 128 + c0;
+          const int ocol = hh * ow + c0;
           ptx::tmem_ld32(tmem_base + lane_addr + kColOut + (uint32_t)ocol, v);
           ptx::tmem_ld_wait();
-          const int d0 = 256 * (int)h + ocol;
+          const int d0 = pair_col0 + ocol;
           if (row_ok) {
             if (d0 + 32 <= P.D) {
 #pragma unroll
@@ -673,7 +681,8 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(l_out_empty);
       }
-      if (row_ok) {   // statistics over MY pair's tiles only: 4 sub-partials per part (pair x column half)
+      const bool stats = (P.ch0 == 0);
+      if (row_ok && stats) {   // statistics over MY pair's tiles only: 4 sub-partials per part (pair x column half)
         const int64_t o = ((int64_t)jp * 4 + 2 * (int)h + hh) * P.slot_rows + gi;
         if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
         if (MODE == M_LUNIF_GRAD) { P.s0[o] = st0; P.s1[o] = st1; }
@@ -682,12 +691,13 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // that finishes the row block clears the slots nobody writes.
       if (row_ok && jb_lo + nt == P.n_jb) {
         for (int sl = jp + 1; sl < P.jparts; ++sl) {
-          const int dbase = 256 * (int)h + hh * 128;
+          const int dbase = pair_col0 + hh * ow;
           float* orow = P.out + ((int64_t)sl * P.slot_rows + gi) * P.D + dbase;
-          for (int cx = 0; cx < 128; cx += 4) {
+          for (int cx = 0; cx < ow; cx += 4) {
             if (dbase + cx + 4 <= P.D) *reinterpret_cast<float4*>(orow + cx) = make_float4(0.f, 0.f, 0.f, 0.f);
             else for (int c2 = 0; c2 < 4; ++c2) if (dbase + cx + c2 < P.D) orow[cx + c2] = 0.f;
           }
+          if (!stats) continue;
           const int64_t o = ((int64_t)sl * 4 + 2 * (int)h + hh) * P.slot_rows + gi;
           if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = 0.f;
           if (MODE == M_LUNIF_GRAD) { P.s0[o] = 0.f; P.s1[o] = 0.f; }
@@ -822,7 +832,8 @@ int scb_quad_clusters() {
   if (n == 0) {
     static std::atomic<unsigned long long> attr_done{0};
     if (scb_opt_in_smem(attr_done, kQuadSmem, k_tc_quad<M_ANCHOR_GRAD, 0>, k_tc_quad<M_ANCHOR_GRAD, 8>,
-                        k_tc_quad<M_LUNIF_GRAD, 0>, k_tc_quad<M_LUNIF_GRAD, 8>) != cudaSuccess) {
+                        k_tc_quad<M_ANCHOR_GRAD, 12>, k_tc_quad<M_ANCHOR_GRAD, 16>, k_tc_quad<M_LUNIF_GRAD, 0>,
+                        k_tc_quad<M_LUNIF_GRAD, 8>, k_tc_quad<M_LUNIF_GRAD, 12>, k_tc_quad<M_LUNIF_GRAD, 16>) != cudaSuccess) {
       cudaGetLastError();
       n = -1;
     } else {
@@ -850,13 +861,14 @@ struct QuadSplit {
   int jparts;
 };
 int scb_tc_flags_get();
-QuadSplit scb_quad_split(int64_t nA, int64_t nB, int n_sm) {
+QuadSplit scb_quad_split(int64_t nA, int64_t nB, int D, int n_sm) {
   QuadSplit q{nA, 0, 1};
   const int n_cl = scb_quad_clusters();
   const int64_t n_jb = (nB + 127) / 128;
   const int side = n_cl > 0 ? (n_sm - 4 * n_cl) / 2 : 0;
   const int64_t n_rb = (nA + 127) / 128;
-  if ((scb_tc_flags_get() & 8) && side >= 2 && n_rb >= 64) {     // measured at 32 row blocks (an 8-GPU shard): 0.256 vs 0.245 ms
+  // (the CTA-pair kernel stops at D = 512: no row split beyond)
+  if ((scb_tc_flags_get() & 8) && side >= 2 && n_rb >= 64 && D <= 512) {     // measured at 32 row blocks (an 8-GPU shard): 0.256 vs 0.245 ms
     int64_t rb_side = (n_rb * SCB_QUAD_SIDE_PERMILLE + 500) / 1000;
     rb_side &= ~(int64_t)1;                                   // the clusters keep whole 256-row blocks
     if (rb_side >= 2 && rb_side < n_rb - 2) {
@@ -919,7 +931,7 @@ int launch_quad_rows(const void* A, int64_t nA, const void* Bm, int64_t nB, int 
   P.kch = (D + 63) / 64;
   P.n_rp = (int)((nA + 255) / 256);
   P.n_jb = (int)((nB + 127) / 128);
-  SCB_CHECK_ARG(P.kch > 4 && P.kch <= 8, SCB_E_SHAPE, "quad kernel needs 256 < D <= 512 (D=%d)", D);
+  SCB_CHECK_ARG(P.kch > 4 && P.kch <= 16, SCB_E_SHAPE, "quad kernel needs 256 < D <= 1024 (D=%d)", D);
   P.fmt = (dtype == SCB_BF16) ? 1 : 0;
   const int budget = kQuadSmem - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
   const int n_astat = P.kch < kAStat ? P.kch : kAStat;
@@ -944,9 +956,19 @@ int launch_quad_rows(const void* A, int64_t nA, const void* Bm, int64_t nB, int 
   scb_quad_span_plan(P.n_rp, P.n_jb, n_cl, &n_used, &P.span, &pmax);
   SCB_CHECK_ARG(P.jparts >= pmax, SCB_E_ARG, "quad kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
                 P.jparts, pmax);
-  if (P.kch == 8) k_tc_quad<MODE, 8><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
-  else k_tc_quad<MODE, 0><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
-  SCB_CHECK_LAUNCH("tc_quad");
+  // Column groups: one launch per 8 output chunks (512 columns).  Every launch recomputes the S tiles over the full D
+  // (MMA1, kch K-chunks) and accumulates its group's columns (MMA2); a last group of <= 4 chunks runs with one chunk per
+  // CTA (MMA2 N = 128) so that all four CTAs keep useful columns (D = 768: 8 + 4 chunks).  Hardware contractions per
+  // sweep: D = 768 -> 2 + 1 = 3 (algorithmic 2), D = 1024 -> 2 + 1 = 3.
+  for (int ch0 = 0; ch0 < P.kch; ch0 += 8) {
+    P.ch0 = ch0;
+    P.cpc = (P.kch - ch0 > 4) ? 2 : 1;
+    if (P.kch == 8) k_tc_quad<MODE, 8><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
+    else if (P.kch == 12) k_tc_quad<MODE, 12><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
+    else if (P.kch == 16) k_tc_quad<MODE, 16><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
+    else k_tc_quad<MODE, 0><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
+    SCB_CHECK_LAUNCH("tc_quad");
+  }
   return 0;
 }
 
@@ -954,7 +976,7 @@ template <int MODE>
 int launch_quad(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
                 QuadParams P, cudaStream_t s) {
   if (nA == 0) return 0;
-  const QuadSplit q = scb_quad_split(nA, nB, scb_num_sms());
+  const QuadSplit q = scb_quad_split(nA, nB, D, scb_num_sms());
   QuadSide* side = q.side_pairs ? quad_side() : nullptr;
   P.slot_rows = nA;
   if (!side) {

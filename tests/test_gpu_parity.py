@@ -120,7 +120,12 @@ def test_bf16_tensor_core_path_matches_golden(name, tc_flags):
                                            # slots, odd output halves), D tails, odd / single tile counts, row tails
                                            (640, 320, 0.1, "corr"), (385, 384, 0.07, "cluster"), (1300, 448, 0.1, "corr"),
                                            (129, 264, 0.1, "iid"), (128, 512, 0.1, "corr"), (2100, 456, 0.05, "cluster"),
-                                           (5000, 512, 0.1, "corr")])
+                                           (5000, 512, 0.1, "corr"),
+                                           # cluster-of-4 kernel with column groups (512 < D <= 1024): a second group of
+                                           # one chunk per CTA (D <= 768, clamped chunks at D = 576) or two (D > 768),
+                                           # D tails, odd tile counts, several row blocks per cluster span
+                                           (640, 576, 0.1, "corr"), (2100, 768, 0.05, "cluster"), (513, 832, 0.07, "cluster"),
+                                           (900, 776, 0.1, "iid"), (1300, 1024, 0.1, "corr"), (4096, 768, 0.1, "corr")])
 def test_tensor_core_path_vs_oracle_on_seeded_inputs(B, D, tau, kind):
     from oracle.make_golden import make_inputs
     I, T = make_inputs(kind, B, D, seed=B + D)
@@ -310,7 +315,9 @@ class _GuardedAlloc:
 
 @pytest.mark.parametrize("B,D,tau,dtype", [(385, 384, 0.07, torch.bfloat16), (129, 264, 0.1, torch.bfloat16), (640, 320, 0.1, torch.float16),
                                            (300, 512, 0.01, torch.bfloat16), (257, 768, 0.1, torch.bfloat16),
-                                           (131, 44, 0.1, torch.float32), (1000, 512, 0.1, torch.bfloat16)])
+                                           (131, 44, 0.1, torch.float32), (1000, 512, 0.1, torch.bfloat16),
+                                           (385, 1000, 0.1, torch.bfloat16), (1000, 768, 0.07, torch.float16),
+                                           (300, 584, 0.1, torch.bfloat16)])
 def test_kernels_stay_inside_their_buffers(B, D, tau, dtype):
     """No out-of-bounds write by any kernel (compute-sanitizer is closed on this pool): all library-side buffers are
     allocated with canary zones around them; tails in rows, columns and D, every K-chunk count of the pair kernel."""

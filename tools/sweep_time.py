@@ -11,7 +11,10 @@ be = scb.get_backend()
 tag = os.environ.get("SCB_LIB_SUFFIX", "") or "default"
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 7
 be.lib.scb_set_tc_flags(flags)
-for (nA, nB, D) in [(32768, 32768, 512), (4096, 32768, 512)]:
+shapes = [(32768, 32768, 512), (4096, 32768, 512)]
+if os.environ.get("SCB_SWEEP_SHAPES"):        # e.g. "8192x65536x768,4096x4096x1024" (rows x columns x D)
+    shapes = [tuple(int(v) for v in t.split("x")) for t in os.environ["SCB_SWEEP_SHAPES"].split(",")]
+for (nA, nB, D) in shapes:
     g = torch.Generator(device="cuda").manual_seed(1)
     X = torch.nn.functional.normalize(torch.randn(nB, D, generator=g, device="cuda"), dim=-1).to(torch.bfloat16)
     Y = torch.nn.functional.normalize(X.float() + 0.5 * torch.randn(nB, D, generator=g, device="cuda"), dim=-1).to(torch.bfloat16)
@@ -32,5 +35,5 @@ for (nA, nB, D) in [(32768, 32768, 512), (4096, 32768, 512)]:
         ts = sorted(a.elapsed_time(b) for _, a, b in be.pass_events)
         be.pass_events = None
         out[name] = (ts[len(ts) // 2], ts[0])
-    print(f"[{tag} flags={flags}] nA={nA}: lunif median {out['lunif'][0]:.3f} min {out['lunif'][1]:.3f} ms ({4.0 * nA * nB * D / out['lunif'][0] / 1e9:.0f} TF/s) | "
-          f"anchor median {out['anchor'][0]:.3f} min {out['anchor'][1]:.3f} ms", flush=True)
+    print(f"[{tag} flags={flags}] nA={nA} nB={nB} D={D}: lunif median {out['lunif'][0]:.3f} min {out['lunif'][1]:.3f} ms ({4.0 * nA * nB * D / out['lunif'][0] / 1e9:.0f} TF/s) | "
+          f"anchor median {out['anchor'][0]:.3f} min {out['anchor'][1]:.3f} ms ({4.0 * nA * nB * D / out['anchor'][0] / 1e9:.0f} TF/s)", flush=True)
