@@ -65,8 +65,10 @@ int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, int n_sm, i
 /* debug/tuning knobs for the TC path: bit0 = keep the weight tile in TMEM (TS-mode MMA) instead of
  * shared memory; bit1 = run the gradient passes on CTA pairs (cluster of 2, weight tile shared through
  * distributed shared memory) when 256 < D <= 512; bit2 = run them on clusters of 4 with cta_group::2
- * MMAs (two row blocks x two output halves) when additionally nA > 128; bit3 = with bit2, give the last rows of a
- * large pass to CTA pairs running concurrently on the SMs that clusters of 4 cannot use.  Returns the previous value. */
+ * MMAs (two row blocks x two output halves) when 256 < D <= 1024 and nA > 128; bit3 = with bit2, give the last rows of a
+ * large pass to CTA pairs running concurrently on the SMs that clusters of 4 cannot use; bit4 = with bit2, passes with
+ * 512 < D <= 768 keep all output columns in TMEM (one S buffer) instead of running once per group of 512 output columns
+ * (768 < D <= 1024 always runs in two groups).  Default: all five bits set.  Returns the previous value. */
 int scb_set_tc_flags(int flags);
 /* Which kernel a TC gradient pass over nA rows of width D runs on the current device:
  * 0 = single CTA (k_tc_pass), 1 = CTA pair (k_tc_pair), 2 = cluster of 4 (k_tc_quad).  In *units (may be

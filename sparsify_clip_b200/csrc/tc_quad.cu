@@ -1,6 +1,10 @@
 // tc_quad.cu -- gradient passes on a CLUSTER OF FOUR CTAs (two cta_group::2 pairs, sm_100a) for 256 < D <= 1024.
-// (D > 512: the output columns are covered by successive launches, "column groups" of up to 8 K-chunks, each of which
-// recomputes the S tiles over the full D -- see launch_quad_rows.)
+// D > 512, two ways (launch_quad_rows):
+//   512 < D <= 768  TRI variant: ONE S buffer, so that the output accumulator may take 384 TMEM columns per CTA
+//                   (OUT 384 | S 128): nothing is recomputed.  MMA2 runs as three N = 128 instructions per K step (one
+//                   64-column chunk per CTA each); the other pair's tile is consumed while the epilogue turns S into W.
+//   768 < D <= 1024 the output columns are covered by two launches, "column groups" of 8 K-chunks, each of which
+//                   recomputes the S tiles over the full D (3 hardware contractions for 2 algorithmic).
 //
 // k_tc_pair (tc_pair.cu) is bound by shared-memory bandwidth, not by the tensor pipe: its MMA1 is a single-CTA
 // M128.N128.K16 SS instruction that reads 8 KB of operands per 64 cycles -- all of an SM's 128 B/clk -- and every
@@ -55,7 +59,7 @@ constexpr int kWBuf = SCB_QUAD_WBUF;          // landing buffers for the other p
 constexpr int kSendPaceClk = SCB_QUAD_PACE;   // idle cycles between two 16-byte remote stores of a sender thread
 constexpr int kPeerLag = SCB_QUAD_LAG;        // MMA2 of the other pair's tile is issued this many steps after the tile (odd)
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColOut = 0, kColS0 = 256;
+constexpr uint32_t kColOut = 0;
 
 struct QuadParams {
   int64_t nA, nB;
@@ -231,11 +235,13 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <int MODE, int KCH>
+template <int MODE, int KCH, bool TRI = false>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 1)
 k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmBh, const QuadParams P) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kNSB = TRI ? 1u : 2u;             // S buffers in TMEM
+  constexpr uint32_t kColS0 = TRI ? 384u : 256u;       // TMEM: OUT [0, kColS0) | S buffers
   const float p0_eff = P.p0_dev ? P.p0 * __ldg(P.p0_dev) : P.p0;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;   // same offset in every CTA
   const int kch = KCH ? KCH : P.kch;
@@ -354,6 +360,14 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // my two 64-wide output chunks of tile tt (clamped into the matrix: columns beyond D are computed from some
       // valid chunk and never stored)
       auto load_v = [&](int tt, int tag) {
+        if constexpr (TRI) {      // three single chunks: MMA2 instruction i takes chunk 4 i + 2 h + c from this CTA
+          for (int i = 0; i < 3; ++i) {
+            int ch = 4 * i + 2 * (int)h + (int)c;
+            if (ch >= kch) ch = kch - 1;
+            load_full(&tmB, ch * 64, (jb_lo + tt) * 128, tag);
+          }
+          return;
+        }
         for (int u = 0; u < 2; ++u) {
           if (u >= P.cpc) { (void)slot_begin(0u, tag); continue; }    // one chunk per CTA: the pair's second slot stays empty
           int ch = P.ch0 + P.cpc * (2 * (int)h + (int)c) + u;
@@ -377,10 +391,15 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             __syncwarp();
           }
-          if (b1_slots & 1) (void)slot_begin(0u, 118);
+          if (!TRI && (b1_slots & 1)) (void)slot_begin(0u, 118);
         }
-        if (t - 2 >= 0 && t - 2 < nt) load_v(t - 2, 121);
-        if (t - kPeerLag >= 0 && t - kPeerLag < nt) load_v(t - kPeerLag, 122);
+        if constexpr (TRI) {     // one S buffer: the own tile's MMA2 follows its MMA1 in the same step, after the other pair's
+          if (t - kPeerLag >= 0 && t - kPeerLag < nt) load_v(t - kPeerLag, 122);
+          if (t < nt) load_v(t, 121);
+        } else {
+          if (t - 2 >= 0 && t - 2 < nt) load_v(t - 2, 121);
+          if (t - kPeerLag >= 0 && t - kPeerLag < nt) load_v(t - kPeerLag, 122);
+        }
       }
     }
   }
@@ -393,7 +412,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t a_full_par = 0, out_empty_par = 1, item_cnt = 0;
       uint32_t k1 = 0, k2 = 0, kp = 0;   // issued MMA1 (own tiles), MMA2 on own tiles, MMA2 on the other pair's tiles
       const uint32_t idesc1 = ptx::idesc_f16(256, 128, P.fmt, P.fmt, 0, 0);
-      const uint32_t idesc2 = ptx::idesc_f16(256, 128 * P.cpc, P.fmt, P.fmt, 0, 1);
+      const uint32_t idesc2 = ptx::idesc_f16(256, TRI ? 128 : 128 * P.cpc, P.fmt, P.fmt, 0, 1);
       const uint32_t a_lo0 = ptx::desc_lo(sm_a, 16);
       const uint32_t w_lo0 = ptx::desc_lo(sm_w, 16);
       const uint32_t ring_lo0 = ptx::desc_lo(sm_ring, 16);
@@ -408,9 +427,9 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         int own_left = n_own;
         auto mma1 = [&]() {
-          const uint32_t b = k1 & 1u;
+          const uint32_t b = k1 % kNSB;
           if (lane == 0) tr.rec(10, k1);
-          mbar_wait_cl(bar(BAR_S_EMPTY + b), ((k1 >> 1) & 1u) ^ 1u, 210);
+          mbar_wait_cl(bar(BAR_S_EMPTY + b), ((k1 / kNSB) & 1u) ^ 1u, 210);
           if (lane == 0) tr.rec(11, k1);
           const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
           auto kpair = [&](int m) {
@@ -453,7 +472,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll 1
             for (int m = 0; m < n_bslots; ++m) kpair(m);
           }
-          if (b1_slots & 1) {     // padding slot (keeps the V pairs on even slots)
+          if (!TRI && (b1_slots & 1)) {     // padding slot (keeps the V pairs on even slots)
             const uint32_t s = ring.take(nslots);
             mbar_wait_cl(bar(BAR_FULL + s), ring.parity_then_flip(s), 213);
             if (ptx::elect_one()) umma_commit2(bar(BAR_EMPTY + s), pair_mask);
@@ -471,8 +490,8 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           uint32_t b = 0;
           if (lane == 0) tr.rec(own ? 20 : 30, own ? k2 : kp);
           if (own) {
-            b = k2 & 1u;
-            mbar_wait_cl(bar(BAR_G_MMA + b), (k2 >> 1) & 1u, 220);
+            b = k2 % kNSB;
+            mbar_wait_cl(bar(BAR_G_MMA + b), (k2 / kNSB) & 1u, 220);
           } else {
             const uint32_t wb = kp % kWBuf, wpar = (kp / kWBuf) & 1u;
             if (ptx::elect_one()) ptx::mbar_expect_tx(bar(BAR_W_FULL + wb), 2u * kSlotBytes);
@@ -487,6 +506,38 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             out_empty_par ^= 1;
           }
           const uint32_t g_tmem = tmem_base + kColS0 + 128u * b;
+          if constexpr (TRI) {
+            // three N = 128 instructions per K step, one ring slot (one 64-column chunk of each CTA) per instruction:
+            // OUT columns [128 i, 128 i + 128) <- output chunks 4 i + 2 h + {0, 1}
+            for (uint32_t i = 0; i < 3; ++i) {
+              const uint32_t sv = ring.take(nslots);
+              mbar_wait_cl(bar(BAR_FULL + sv), ring.parity_then_flip(sv), 222);
+              ptx::tc_fence_after();
+              const uint32_t vlo = ring_v_lo0 + sv * kChunkLo;
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (uint32_t ks = 0; ks < 8; ++ks) {
+                  const uint64_t bdesc = ptx::desc_join(vlo + 128u * ks);
+                  const uint32_t accum = (uint32_t)!(first && ks == 0);
+                  const uint32_t d_tmem = tmem_base + kColOut + 128u * i;
+                  if (own)
+                    umma_ts2(d_tmem, g_tmem + (ks >> 2) * 64u + (ks & 3u) * 8u, bdesc, idesc2, accum);
+                  else
+                    umma_ss2(d_tmem, ptx::desc_join(w_lo0 + (2u * (kp % kWBuf) + (ks >> 2)) * kChunkLo + (ks & 3u) * 2u), bdesc, idesc2, accum);
+                }
+                umma_commit2(bar(BAR_EMPTY + sv), pair_mask);
+                if (i == 2) {
+                  if (own) umma_commit2(bar(BAR_S_EMPTY + b), (uint16_t)(1u << lead_rank));
+                  else umma_commit2(bar(BAR_W_EMPTY + (kp % kWBuf)), xpair_mask);
+                  if (last) umma_commit2(bar(BAR_OUT_FULL), pair_mask);
+                }
+              }
+              __syncwarp();
+            }
+            if (lane == 0) tr.rec(own ? 23 : 33, own ? k2 : kp);
+            if (own) ++k2; else ++kp;
+            return;
+          }
           const uint32_t sv = ring.take(nslots);
           mbar_wait_cl(bar(BAR_FULL + sv), ring.parity_then_flip(sv), 222);
           const uint32_t sv1 = ring.take(nslots);
@@ -518,8 +569,13 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         int m2_left = nt;          // the first MMA2 of the item overwrites OUT, the last one publishes it
         for (int t = t_first; t < nt + kPeerLag + 1; t += 2) {
           if (t < nt) mma1();
-          if (t - 2 >= 0 && t - 2 < nt) { mma2(true, m2_left == nt, m2_left == 1); --m2_left; }
-          if (t - kPeerLag >= 0 && t - kPeerLag < nt) { mma2(false, m2_left == nt, m2_left == 1); --m2_left; }
+          if constexpr (TRI) {   // the other pair's tile keeps the tensor pipe busy while the epilogue turns S(t) into W(t)
+            if (t - kPeerLag >= 0 && t - kPeerLag < nt) { mma2(false, m2_left == nt, m2_left == 1); --m2_left; }
+            if (t < nt) { mma2(true, m2_left == nt, m2_left == 1); --m2_left; }
+          } else {
+            if (t - 2 >= 0 && t - 2 < nt) { mma2(true, m2_left == nt, m2_left == 1); --m2_left; }
+            if (t - kPeerLag >= 0 && t - kPeerLag < nt) { mma2(false, m2_left == nt, m2_left == 1); --m2_left; }
+          }
         }
       }
     } else {
@@ -568,7 +624,8 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int64_t my_diag_col = gi + P.diag_off;
 
       for (int t = t_first; t < nt; t += 2, ++ke) {
-        const uint32_t b = ke & 1u;
+        const uint32_t b = ke % kNSB;          // S buffer
+        const uint32_t cb2 = ke & 1u;          // column-vector buffer (always double: a warp may run one tile ahead)
         const int jb = jb_lo + t;
         const int64_t col0 = (int64_t)jb * 128 + 64 * hh;
         const bool tile_partial = ((int64_t)jb * 128 + 128) > P.nB;
@@ -578,12 +635,12 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int64_t gj = (int64_t)jb * 128 + idx;
             float cv = INFINITY;
             if (gj < P.nB) cv = (MODE == M_ANCHOR_GRAD) ? P.colvec[gj] * SCB_LOG2E : P.colvec[gj] * p0_eff;
-            cbuf[b * 128 + idx] = cv;
+            cbuf[cb2 * 128 + idx] = cv;
           }
           ptx::named_bar_sync(1, kEpiThreads);
         }
         if (lane == 0) tr.rec(40, ke);
-        ptx::mbar_wait(bar(BAR_S_FULL + b), (ke >> 1) & 1u, 300);
+        ptx::mbar_wait(bar(BAR_S_FULL + b), (ke / kNSB) & 1u, 300);
         if (lane == 0) tr.rec(41, ke);
         ptx::tc_fence_after();
         const int64_t drow0 = (int64_t)row0 + 32 * q + P.diag_off;
@@ -596,7 +653,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           ptx::tmem_ld32(tmem_base + lane_addr + kColS0 + 128u * b + 64u * hh + 32u * cc, v);
           ptx::tmem_ld_wait();
           const int64_t cbase = col0 + 32 * cc;
-          const float* cb = cbuf + b * 128 + 64 * hh + 32 * cc;
+          const float* cb = cbuf + cb2 * 128 + 64 * hh + 32 * cc;
           const int dcol = diag_here ? (int)(my_diag_col - cbase) : -1;
           if (tile_partial && MODE == M_ANCHOR_GRAD) {
             const int nvalid = (int)min((int64_t)32, max((int64_t)0, P.nB - cbase));
@@ -651,19 +708,23 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
       }  // own tiles
 
-      // ---- drain my quarter of the output accumulator (my 128 rows x my pair's 128 cpc columns)
-      const int ow = 64 * P.cpc;                                // output columns this warp drains
-      const int pair_col0 = 64 * (P.ch0 + 2 * P.cpc * (int)h);  // first output column of my pair in this column group
+      // ---- drain my share of the output accumulator (my 128 rows; this warp: `n_runs` runs of `ow` columns).
+      // Column groups: one run, TMEM columns [hh ow, +ow) <-> output columns 64 (ch0 + 2 cpc h) + the same offset.
+      // TRI: run i = the i-th MMA2 instruction: TMEM columns [128 i + 64 hh, +64) <-> output columns 64 (4 i + 2 h) + 64 hh.
+      const int n_runs = TRI ? 3 : 1;
+      const int ow = TRI ? 64 : 64 * P.cpc;
+      auto run_tcol = [&](int i) -> int { return TRI ? 128 * i + 64 * hh : hh * ow; };
+      auto run_gcol = [&](int i) -> int { return TRI ? 64 * (4 * i + 2 * (int)h) + 64 * hh : 64 * (P.ch0 + 2 * P.cpc * (int)h) + hh * ow; };
       if (nt > 0) {
         ptx::mbar_wait(bar(BAR_OUT_FULL), item_cnt & 1u, 320);
         ptx::tc_fence_after();
         float* orow = P.out + ((int64_t)jp * P.slot_rows + gi) * P.D;
-        for (int c0 = 0; c0 < ow; c0 += 32) {
+        for (int rc = 0; rc < n_runs * (ow / 32); ++rc) {
           uint32_t v[32];
-          const int ocol = hh * ow + c0;
-          ptx::tmem_ld32(tmem_base + lane_addr + kColOut + (uint32_t)ocol, v);
+          const int ri = rc / (ow / 32), c0 = 32 * (rc % (ow / 32));
+          ptx::tmem_ld32(tmem_base + lane_addr + kColOut + (uint32_t)(run_tcol(ri) + c0), v);
           ptx::tmem_ld_wait();
-          const int d0 = pair_col0 + ocol;
+          const int d0 = run_gcol(ri) + c0;
           if (row_ok) {
             if (d0 + 32 <= P.D) {
 #pragma unroll
@@ -681,7 +742,7 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(l_out_empty);
       }
-      const bool stats = (P.ch0 == 0);
+      const bool stats = TRI || (P.ch0 == 0);
       if (row_ok && stats) {   // statistics over MY pair's tiles only: 4 sub-partials per part (pair x column half)
         const int64_t o = ((int64_t)jp * 4 + 2 * (int)h + hh) * P.slot_rows + gi;
         if (MODE == M_ANCHOR_GRAD && P.s0) P.s0[o] = st0;
@@ -691,11 +752,13 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       // that finishes the row block clears the slots nobody writes.
       if (row_ok && jb_lo + nt == P.n_jb) {
         for (int sl = jp + 1; sl < P.jparts; ++sl) {
-          const int dbase = pair_col0 + hh * ow;
-          float* orow = P.out + ((int64_t)sl * P.slot_rows + gi) * P.D + dbase;
-          for (int cx = 0; cx < ow; cx += 4) {
-            if (dbase + cx + 4 <= P.D) *reinterpret_cast<float4*>(orow + cx) = make_float4(0.f, 0.f, 0.f, 0.f);
-            else for (int c2 = 0; c2 < 4; ++c2) if (dbase + cx + c2 < P.D) orow[cx + c2] = 0.f;
+          for (int ri = 0; ri < n_runs; ++ri) {
+            const int dbase = run_gcol(ri);
+            float* orow = P.out + ((int64_t)sl * P.slot_rows + gi) * P.D + dbase;
+            for (int cx = 0; cx < ow; cx += 4) {
+              if (dbase + cx + 4 <= P.D) *reinterpret_cast<float4*>(orow + cx) = make_float4(0.f, 0.f, 0.f, 0.f);
+              else for (int c2 = 0; c2 < 4; ++c2) if (dbase + cx + c2 < P.D) orow[cx + c2] = 0.f;
+            }
           }
           if (!stats) continue;
           const int64_t o = ((int64_t)sl * 4 + 2 * (int)h + hh) * P.slot_rows + gi;
@@ -719,8 +782,8 @@ k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     SCB_QUAD_FOR_SEGMENTS() {
       SCB_QUAD_ITEM_SETUP();
       for (int t = t_first; t < nt; t += 2, ++kx) {
-        const uint32_t b = kx & 1u;
-        ptx::mbar_wait(bar(BAR_G_FULL + b), (kx >> 1) & 1u, 400);
+        const uint32_t b = kx % kNSB;
+        ptx::mbar_wait(bar(BAR_G_FULL + b), (kx / kNSB) & 1u, 400);
         if (lane == 0) tr.rec(50, kx);
         ptx::tc_fence_after();
         uint32_t w0[32], w1[32];     // the two 64-column halves of my 32 rows of W (packed 16-bit pairs)
@@ -833,7 +896,9 @@ int scb_quad_clusters() {
     static std::atomic<unsigned long long> attr_done{0};
     if (scb_opt_in_smem(attr_done, kQuadSmem, k_tc_quad<M_ANCHOR_GRAD, 0>, k_tc_quad<M_ANCHOR_GRAD, 8>,
                         k_tc_quad<M_ANCHOR_GRAD, 12>, k_tc_quad<M_ANCHOR_GRAD, 16>, k_tc_quad<M_LUNIF_GRAD, 0>,
-                        k_tc_quad<M_LUNIF_GRAD, 8>, k_tc_quad<M_LUNIF_GRAD, 12>, k_tc_quad<M_LUNIF_GRAD, 16>) != cudaSuccess) {
+                        k_tc_quad<M_LUNIF_GRAD, 8>, k_tc_quad<M_LUNIF_GRAD, 12>, k_tc_quad<M_LUNIF_GRAD, 16>,
+                        k_tc_quad<M_ANCHOR_GRAD, 0, true>, k_tc_quad<M_ANCHOR_GRAD, 12, true>,
+                        k_tc_quad<M_LUNIF_GRAD, 0, true>, k_tc_quad<M_LUNIF_GRAD, 12, true>) != cudaSuccess) {
       cudaGetLastError();
       n = -1;
     } else {
@@ -956,6 +1021,16 @@ int launch_quad_rows(const void* A, int64_t nA, const void* Bm, int64_t nB, int 
   scb_quad_span_plan(P.n_rp, P.n_jb, n_cl, &n_used, &P.span, &pmax);
   SCB_CHECK_ARG(P.jparts >= pmax, SCB_E_ARG, "quad kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
                 P.jparts, pmax);
+  // 512 < D <= 768: the single-S-buffer variant holds all 384 output columns of a pair in TMEM -- one launch, nothing
+  // recomputed (tc_flags bit4; off = column groups, kept as the A/B reference).
+  if (P.kch > 8 && P.kch <= 12 && (scb_tc_flags_get() & 16)) {
+    P.ch0 = 0;
+    P.cpc = 2;
+    if (P.kch == 12) k_tc_quad<MODE, 12, true><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
+    else k_tc_quad<MODE, 0, true><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);
+    SCB_CHECK_LAUNCH("tc_quad (single S buffer)");
+    return 0;
+  }
   // Column groups: one launch per 8 output chunks (512 columns).  Every launch recomputes the S tiles over the full D
   // (MMA1, kch K-chunks) and accumulates its group's columns (MMA2); a last group of <= 4 chunks runs with one chunk per
   // CTA (MMA2 N = 128) so that all four CTAs keep useful columns (D = 768: 8 + 4 chunks).  Hardware contractions per
