@@ -50,7 +50,7 @@ extern "C" {
 
 /* ABI revision of this header.  scb_version() returns the revision the loaded library was BUILT against; a binding
  * must refuse a library whose revision differs (argument lists may have changed). */
-#define SCB_ABI_VERSION 201
+#define SCB_ABI_VERSION 202
 int scb_version(void);
 /* Device-resident temperature.  Every entry that takes the logit scale 1/tau as a host float (`scale`, and the
  * coefficients derived from it) also takes `const float* scale_dev` as its last argument before the stream: when non-NULL
@@ -267,6 +267,11 @@ int scb_peer_close(void* ptr, int opened);
 int scb_peer_begin(int* epoch, const int* done, int world, void* stream);
 int scb_peer_push(const void* src, int64_t bytes, void* const* dst, int n, const int* epoch, int* const* arrived_words,
                   int world, void* stream);
+/* scb_peer_push with the copies done by the SMs (16-byte stores over NVLink, every destination written by one kernel;
+ * the last CTA publishes the flags): for the gather a step starts with, when no sweep occupies the SMs yet.
+ * counter: zero-initialised device word owned by the role (every launch leaves it at zero).  bytes % 16 == 0. */
+int scb_peer_push_sm(const void* src, int64_t bytes, void* const* dst, int n, const int* epoch, int* const* arrived_words,
+                     int world, unsigned* counter, void* stream);
 /* the copies of scb_peer_push alone (several streams may share a large shard's pushes; scb_peer_push with n = 0 sends the flags) */
 int scb_peer_copy(const void* src, int64_t bytes, void* const* dst, int n, void* stream);
 int scb_peer_wait(const int* epoch, const int* arrived, int world, void* stream);

@@ -60,6 +60,7 @@ SIGNATURES = {
     "scb_peer_close": [_vp, _i32],
     "scb_peer_begin": [_vp, _vp, _i32, _vp],
     "scb_peer_push": [_vp, _i64, ctypes.POINTER(ctypes.c_void_p), _i32, _vp, _vp, _i32, _vp],
+    "scb_peer_push_sm": [_vp, _i64, ctypes.POINTER(ctypes.c_void_p), _i32, _vp, _vp, _i32, _vp, _vp],
     "scb_peer_copy": [_vp, _i64, ctypes.POINTER(ctypes.c_void_p), _i32, _vp],
     "scb_peer_wait": [_vp, _vp, _i32, _vp],
     "scb_peer_release": [_vp, _vp, _i32, _vp],

@@ -26,7 +26,17 @@ import torch.distributed as dist
 from . import _lib
 from ._lib import check
 
-_state = {"mode": os.environ.get("SCB_GATHER", "auto"), "objs": {}, "ok": {}, "open": []}
+_state = {"mode": os.environ.get("SCB_GATHER", "auto"), "objs": {}, "ok": {}, "open": [],
+          # roles whose pushes are done by the SMs instead of the copy engines (scb_peer_push_sm): the gather a step starts
+          # with, when no sweep occupies the SMs yet.  SCB_PEER_SM_ROLES="" turns it off, "I,T" widens it.
+          "sm_roles": {r for r in os.environ.get("SCB_PEER_SM_ROLES", "I").split(",") if r}}
+_SM_PUSH_MIN_BYTES = 1 << 18          # below this the copy engines' fixed cost is what counts either way
+
+
+def set_sm_push_roles(roles):
+    """Roles ('I', 'T', 'C', ...) pushed by an SM kernel; returns the previous set.  Takes effect for the next gather."""
+    prev, _state["sm_roles"] = _state["sm_roles"], set(roles)
+    return prev
 
 
 def set_gather(mode):
@@ -58,9 +68,9 @@ class _Handle:
 class PeerGather:
     """One role's gather buffer on every rank of `group` (all ranks on this node)."""
 
-    def __init__(self, group, shard_bytes, device):
+    def __init__(self, group, shard_bytes, device, role=None):
         self.lib = _lib.load()
-        self.group, self.device = group, device
+        self.group, self.device, self.role = group, device, role
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 32:
             raise RuntimeError("peer gather supports up to 32 ranks")
@@ -94,6 +104,7 @@ class PeerGather:
         nfan = int(os.environ.get("SCB_PEER_FAN", "0"))
         self.fan = [torch.cuda.Stream(device=device) for _ in range(nfan)] if self.shard >= (1 << 20) and self.world > 2 else []
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)      # CTA counter of scb_peer_push_sm
         i64 = dict(dtype=torch.int64, device=device)
         self.arrived_words = torch.tensor([p + self.arr_off + 4 * self.rank for p in self.ptrs], **i64)
         self.done_words = torch.tensor([p + self.done_off + 4 * self.rank for p in self.ptrs], **i64)
@@ -116,7 +127,12 @@ class PeerGather:
         self.stream.wait_stream(cur)           # x is ready, the epoch is advanced, the peers have released their buffers
         # (x is kept alive by the handle until wait() is enqueued: the wait kernel only passes once my own pushes -- the
         #  last thing to read x -- have set my arrived flag, and any reuse of x's memory is ordered after it on `cur`)
-        if self.fan:
+        if (self.role in _state["sm_roles"] and self.shard >= _SM_PUSH_MIN_BYTES and self.shard % 16 == 0
+                and x.data_ptr() % 16 == 0):
+            check(self.lib.scb_peer_push_sm(x.data_ptr(), self.shard, self._dst, self.world, self.epoch.data_ptr(),
+                                            self.arrived_words.data_ptr(), self.world, self.counter.data_ptr(),
+                                            self.stream.cuda_stream), "peer_push_sm")
+        elif self.fan:
             for k, st in enumerate(self.fan):      # copies only (n destinations, no flag: world = 0 skips nothing but the
                 st.wait_stream(self.stream)        # signal is sent once, below, after every fan stream has been joined)
                 check(self.lib.scb_peer_copy(x.data_ptr(), self.shard, self._fan_dst[k + 1], len(self._fan_dst[k + 1]),
@@ -204,7 +220,7 @@ def all_gather_async(x, group, role):
     if pg is None:
         if capturing:
             return None                       # buffers must exist before a capture (run one eager step first)
-        pg = _state["objs"][key] = PeerGather(group, nbytes, x.device)
+        pg = _state["objs"][key] = PeerGather(group, nbytes, x.device, role)
     flat, h = pg.gather(x)
     out = flat.view(x.dtype).view((pg.world * x.shape[0],) + tuple(x.shape[1:]))
     return out, h
