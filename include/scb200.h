@@ -68,7 +68,9 @@ int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, int n_sm, i
  * MMAs (two row blocks x two output halves) when 256 < D <= 1024 and nA > 128; bit3 = with bit2, give the last rows of a
  * large pass to CTA pairs running concurrently on the SMs that clusters of 4 cannot use; bit4 = with bit2, passes with
  * 512 < D <= 768 keep all output columns in TMEM (one S buffer) instead of running once per group of 512 output columns
- * (768 < D <= 1024 always runs in two groups).  Default: all five bits set.  Returns the previous value. */
+ * (768 < D <= 1024 always runs in two groups); bit5 = use the row-block-aligned work split of the cluster-of-4 kernel
+ * whatever the operand size (by default only when the column operand exceeds 64 MB, i.e. does not stay in L2).
+ * Default: bits 0-4 set.  Returns the previous value. */
 int scb_set_tc_flags(int flags);
 /* Which kernel a TC gradient pass over nA rows of width D runs on the current device:
  * 0 = single CTA (k_tc_pass), 1 = CTA pair (k_tc_pair), 2 = cluster of 4 (k_tc_quad).  In *units (may be

@@ -26,7 +26,7 @@ int scb_tc_set_flags(int);
 int scb_tc_grad_kernel(int64_t nA, int D, int grad);
 int scb_quad_clusters();
 void scb_pair_span_plan(int64_t n_rb, int64_t n_jb, int n_sm, int* n_pairs, int64_t* span, int* pmax);
-void scb_quad_span_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int* n_used, int64_t* span, int* pmax);
+void scb_quad_span_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int align, int* n_used, int64_t* span, int* pmax);
 struct QuadSplit { int64_t rows_quad; int side_pairs; int jparts; };
 QuadSplit scb_quad_split(int64_t nA, int64_t nB, int D, int n_sm);
 

@@ -598,6 +598,7 @@ std::atomic<int> g_tc_flags{31};   // bit0: weight tile in TMEM (TS-mode MMA2) -
                       // bit3: with bit2, the last rows of a large pass run on CTA pairs on the SMs clusters of 4 strand
                       // bit4: with bit2, 512 < D <= 768 runs the single-S-buffer variant (all 384 output columns of a pair
                       //       in TMEM, nothing recomputed) instead of two column-group launches
+                      // bit5: (tests) the cluster-of-4 kernel's row-block-aligned span plan for any operand size
 
 template <int MODE>
 int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
@@ -650,7 +651,7 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
 
 int scb_tc_pair_set_dbg(int);
 int scb_quad_clusters();
-int scb_tc_set_flags(int flags) { const int o = g_tc_flags.exchange(flags & 31); scb_tc_pair_set_dbg(flags >> 5); return o; }
+int scb_tc_set_flags(int flags) { const int o = g_tc_flags.exchange(flags & 63); scb_tc_pair_set_dbg(flags >> 6); return o; }
 int scb_tc_flags_get() { return g_tc_flags.load(); }
 int scb_make_tmap_2d(CUtensorMap* m, const void* base, int64_t rows, int D, int64_t ld, int dtype) {
   return make_tmap(m, base, rows, D, ld, dtype);

@@ -146,6 +146,41 @@ def test_tensor_core_path_vs_oracle_on_seeded_inputs(B, D, tau, kind):
     assert _rel(tp.grad.item(), dtau) <= 1e-3
 
 
+@pytest.mark.parametrize("B,D,tau", [(2100, 768, 0.05), (5000, 512, 0.1), (1300, 1024, 0.1), (700, 640, 0.07)])
+def test_row_block_aligned_spans_of_the_cluster_kernel(B, D, tau):
+    """The work split used when the column operand does not fit in L2 (whole row blocks per cluster, one partial slot;
+    tc_flags bit5 forces it at test sizes): same results as the equal-span split, and inside the oracle gate."""
+    from oracle.make_golden import make_inputs
+    I, T = make_inputs("cluster", B, D, seed=B + D)
+    I, T = I.to(torch.bfloat16).float(), T.to(torch.bfloat16).float()      # bf16-exact values, fp32 gradients back
+    be = scb.get_backend()
+    w = dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0)
+    got = {}
+    for flags in (31, 63):
+        prev = be.lib.scb_set_tc_flags(flags)
+        prev_mode = scb.set_fp32_mode("bf16")
+        try:
+            Ig, Tg = I.cuda().requires_grad_(True), T.cuda().requires_grad_(True)
+            tp = torch.nn.Parameter(torch.tensor(tau))
+            loss = scb.weighted_loss(Ig, Tg, tp, w)
+            loss.backward()
+            got[flags] = (loss.item(), Ig.grad.double().cpu().numpy(), Tg.grad.double().cpu().numpy(), tp.grad.item())
+        finally:
+            scb.set_fp32_mode(prev_mode)
+            be.lib.scb_set_tc_flags(prev)
+    ref, dI, dT, dtau, terms = cf.weighted_loss(I.numpy(), T.numpy(), tau, 1.0, 1.0, 0.5, 0.5, 0.0)
+    mag = sum(abs(v) for v in terms.values())
+    for flags, (l, gI, gT, gt) in got.items():
+        assert abs(l - ref) <= LOSS_RTOL * mag, (flags, l, ref)
+        assert np.linalg.norm(gI - dI) / np.linalg.norm(dI) <= 1e-3, flags
+        assert np.linalg.norm(gT - dT) / np.linalg.norm(dT) <= 1e-3, flags
+        assert _rel(gt, dtau) <= 1e-3, flags
+    # the two splits differ only in where the fp32 partial sums are cut
+    assert abs(got[31][0] - got[63][0]) <= 1e-6 * mag
+    assert np.linalg.norm(got[31][1] - got[63][1]) <= 1e-5 * np.linalg.norm(dI)
+    assert np.linalg.norm(got[31][2] - got[63][2]) <= 1e-5 * np.linalg.norm(dT)
+
+
 def test_full_size_properties_c3():
     """B = 32768, D = 512 (BASELINE c3) -- too big for the dense oracle; size-independent properties:
     translation invariance of L_unif (gradient rows sum to 0), Euler homogeneity of the anchor

@@ -12,6 +12,8 @@ be.lib.scb_set_tc_flags(int(sys.argv[1]) if len(sys.argv) > 1 else 7)
 which = sys.argv[2] if len(sys.argv) > 2 else "lunif"
 nA = nB = 32768
 D = 512
+if os.environ.get("SCB_SWEEP_SHAPE"):          # rows x columns x D, e.g. 8192x65536x768 (c4's 8-GPU shard)
+    nA, nB, D = (int(v) for v in os.environ["SCB_SWEEP_SHAPE"].split("x"))
 g = torch.Generator(device="cuda").manual_seed(1)
 X = torch.nn.functional.normalize(torch.randn(nB, D, generator=g, device="cuda"), dim=-1).to(torch.bfloat16)
 Y = torch.nn.functional.normalize(X.float() + 0.5 * torch.randn(nB, D, generator=g, device="cuda"), dim=-1).to(torch.bfloat16)
@@ -19,10 +21,10 @@ r = torch.full((nA,), 8.0, device="cuda")
 c = torch.full((nB,), 8.0, device="cuda")
 for _ in range(5):
     if which == "lunif":
-        be.lunif_core(X, X, 2.0, 0, True)
+        be.lunif_core(X[:nA], X, 2.0, 0, True)
     elif which == "anchor":
-        be.anchor_grad_pass(X, Y, 10.0, r, c, 0, True)
+        be.anchor_grad_pass(X[:nA], Y, 10.0, r, c, 0, True)
     else:
-        be.lse_rows_cols(X, Y, 10.0)
+        be.lse_rows_cols(X[:nA], Y, 10.0)
 torch.cuda.synchronize()
 print("done")

@@ -1,6 +1,7 @@
 """Record the per-role timeline of cluster 0 of one cluster-of-4 L_unif sweep (debug aid for csrc/tc_quad.cu; needs a
 library built with SCB_DEV=1).  Prints, per leader CTA, where the MMA issuer's time goes per step.
-usage (GPU box): SCB_DEV=1 python sparsify_clip_b200/build.py --force; python tools/quad_trace.py > gpurun_out/quad_trace.log"""
+usage (GPU box): SCB_DEV=1 python sparsify_clip_b200/build.py --force; python tools/quad_trace.py [B [D [tc_flags]]] > gpurun_out/quad_trace.log
+(512 < D <= 768 with tc_flags 31 traces the single-S-buffer variant: ideal 6144 cycles per step there)"""
 import os
 import sys
 from collections import defaultdict
@@ -14,7 +15,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 CAP = 4096
 be = scb.get_backend()
-be.lib.scb_set_tc_flags(7)
+be.lib.scb_set_tc_flags(int(sys.argv[3]) if len(sys.argv) > 3 else 7)
 g = torch.Generator(device="cuda").manual_seed(42)
 X = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device="cuda"), dim=-1).to(torch.bfloat16)
 for _ in range(2):
