@@ -39,11 +39,11 @@ constexpr int kThreads = 512;
 constexpr int kEpiThreads = 256;
 constexpr int kSlotBytes = 128 * 64 * 2;   // one [128 x 64] 16-bit chunk (or two [64 x 64] half-tile chunks)
 constexpr int kHalfBytes = kSlotBytes / 2;
-constexpr int kMaxSlots = 8;
+constexpr int kMaxSlots = 12;
 #ifndef SCB_QUAD_ASTAT
 #define SCB_QUAD_ASTAT 4
 #endif
-constexpr int kAStat = SCB_QUAD_ASTAT;     // K-chunks of the row block resident in smem; the rest stream with the tiles
+constexpr int kAStatDef = SCB_QUAD_ASTAT;     // K-chunks of the row block resident in smem; the rest stream with the tiles
 #ifndef SCB_QUAD_PACE
 #define SCB_QUAD_PACE 100
 #endif
@@ -53,11 +53,25 @@ constexpr int kAStat = SCB_QUAD_ASTAT;     // K-chunks of the row block resident
 #ifndef SCB_QUAD_WBUF
 #define SCB_QUAD_WBUF 2
 #endif
-constexpr int kWBuf = SCB_QUAD_WBUF;          // landing buffers for the other pair's weight tile (1 or 2).  With ONE buffer the
+constexpr int kWBufDef = SCB_QUAD_WBUF;          // landing buffers for the other pair's weight tile (1 or 2).  With ONE buffer the
                                               // hand-over is a serial chain -- consume, release, 32 KB of remote stores (~4200
                                               // cycles measured), consume -- and that chain, not the tensor pipe, set the period
 constexpr int kSendPaceClk = SCB_QUAD_PACE;   // idle cycles between two 16-byte remote stores of a sender thread
-constexpr int kPeerLag = SCB_QUAD_LAG;        // MMA2 of the other pair's tile is issued this many steps after the tile (odd)
+constexpr int kPeerLagDef = SCB_QUAD_LAG;        // MMA2 of the other pair's tile is issued this many steps after the tile (odd)
+// The single-S-buffer variant (512 < D <= 768) has longer steps (6144 MMA cycles) and more to stream per step, and is
+// bound by what the ring can keep in flight: one landing buffer (the hand-over chain fits in a step), peer lag 3 and two
+// resident row-block chunks leave a ring of 10 slots.  Measured at c4's shard (8192 x 65536 x 768), L_unif / anchor sweep:
+// 2 buffers, lag 5, 4 resident (ring 6): 1.354 / 1.614 ms; 1 buffer, lag 3, 4 resident (ring 8): 1.229 / 1.428;
+// 1 buffer, lag 3, 2 resident (ring 10): 1.242 / 1.341; the same settings at D = 512 are 15-25 % SLOWER than the defaults.
+#ifndef SCB_TRI_ASTAT
+#define SCB_TRI_ASTAT 2
+#endif
+#ifndef SCB_TRI_WBUF
+#define SCB_TRI_WBUF 1
+#endif
+#ifndef SCB_TRI_LAG
+#define SCB_TRI_LAG 3
+#endif
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColOut = 0;
 
@@ -240,6 +254,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 1)
 k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmBh, const QuadParams P) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int kAStat = TRI ? SCB_TRI_ASTAT : kAStatDef;
+  constexpr int kWBuf = TRI ? SCB_TRI_WBUF : kWBufDef;
+  constexpr int kPeerLag = TRI ? SCB_TRI_LAG : kPeerLagDef;
+  static_assert(kPeerLag % 2 == 1 && (kWBuf == 1 || kWBuf == 2), "peer lag must be odd; one or two landing buffers");
   constexpr uint32_t kNSB = TRI ? 1u : 2u;             // S buffers in TMEM
   constexpr uint32_t kColS0 = TRI ? 384u : 256u;       // TMEM: OUT [0, kColS0) | S buffers
   const float p0_eff = P.p0_dev ? P.p0 * __ldg(P.p0_dev) : P.p0;
@@ -1021,6 +1039,10 @@ int launch_quad_rows(const void* A, int64_t nA, const void* Bm, int64_t nB, int 
   SCB_CHECK_ARG(P.kch > 4 && P.kch <= 16, SCB_E_SHAPE, "quad kernel needs 256 < D <= 1024 (D=%d)", D);
   P.fmt = (dtype == SCB_BF16) ? 1 : 0;
   const int budget = kQuadSmem - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/;
+  // 512 < D <= 768: the single-S-buffer variant holds all 384 output columns of a pair in TMEM -- one launch, nothing
+  // recomputed (tc_flags bit4; off = column groups, kept as the A/B reference).
+  const bool tri = P.kch > 8 && P.kch <= 12 && (scb_tc_flags_get() & 16);
+  const int kAStat = tri ? SCB_TRI_ASTAT : kAStatDef, kWBuf = tri ? SCB_TRI_WBUF : kWBufDef;
   const int n_astat = P.kch < kAStat ? P.kch : kAStat;
   int nslots = (budget - (n_astat + 2 * kWBuf) * kSlotBytes) / kSlotBytes;
   nslots &= ~1;
@@ -1043,9 +1065,7 @@ int launch_quad_rows(const void* A, int64_t nA, const void* Bm, int64_t nB, int 
   scb_quad_span_plan(P.n_rp, P.n_jb, n_cl, scb_quad_align_spans(nB, D), &n_used, &P.span, &pmax);
   SCB_CHECK_ARG(P.jparts >= pmax, SCB_E_ARG, "quad kernel: jparts=%d but the span plan needs %d partial slots (scb_pass_plan)",
                 P.jparts, pmax);
-  // 512 < D <= 768: the single-S-buffer variant holds all 384 output columns of a pair in TMEM -- one launch, nothing
-  // recomputed (tc_flags bit4; off = column groups, kept as the A/B reference).
-  if (P.kch > 8 && P.kch <= 12 && (scb_tc_flags_get() & 16)) {
+  if (tri) {
     P.ch0 = 0;
     P.cpc = 2;
     if (P.kch == 12) k_tc_quad<MODE, 12, true><<<4 * n_used, kThreads, smem, s>>>(tmA, tmB, tmBh, P);

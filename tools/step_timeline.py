@@ -1,4 +1,4 @@
-"""GPU timeline of one c3 step via torch.profiler (CUPTI): kernel start/duration and idle gaps between kernels."""
+"""GPU timeline of one c3 (or, PROF_CONFIG=c4 PROF_B=65536 PROF_D=768, c4) step via torch.profiler (CUPTI): kernel start/duration and idle gaps between kernels."""
 import os
 import sys
 
@@ -8,18 +8,22 @@ from torch.profiler import ProfilerActivity, profile
 
 import sparsify_clip_b200 as scb
 
-B, D = int(os.environ.get("PROF_B", "32768")), 512
+B, D = int(os.environ.get("PROF_B", "32768")), int(os.environ.get("PROF_D", "512"))
 g = torch.Generator(device="cuda").manual_seed(42)
 I = torch.nn.functional.normalize(torch.randn(B, D, generator=g, device="cuda"), dim=-1)
 T = torch.nn.functional.normalize(I + 0.5 * torch.randn(B, D, generator=g, device="cuda"), dim=-1)
 I = I.to(torch.bfloat16).requires_grad_(True)
 T = T.to(torch.bfloat16).requires_grad_(True)
 w = dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0)
+tau = 0.1
+if os.environ.get("PROF_CONFIG") == "c4":        # exp 10 mid-schedule, learnable CPU temperature (PROF_B=65536 PROF_D=768)
+    w = dict(anchor=1.0, align=1.2, unif_img=0.0, unif_txt=0.0, unif_cen=0.2)
+    tau = torch.nn.Parameter(torch.tensor(0.1))
 
 
 def step():
     I.grad = T.grad = None
-    loss = scb.weighted_loss(I, T, 0.1, w)
+    loss = scb.weighted_loss(I, T, tau, w)
     loss.backward()
     return loss
 
