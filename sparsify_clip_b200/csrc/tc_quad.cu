@@ -72,6 +72,9 @@ constexpr int kPeerLagDef = SCB_QUAD_LAG;        // MMA2 of the other pair's til
 #ifndef SCB_TRI_LAG
 #define SCB_TRI_LAG 3
 #endif
+#ifndef SCB_QUAD_LONG_GROUPS
+#define SCB_QUAD_LONG_GROUPS 1      // the column-group launches of D = 768 / 1024 (KCH 12 / 16) use the same settings (D = 1024 shard sweep: 768 -> 869 TF/s)
+#endif
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColOut = 0;
 
@@ -254,9 +257,10 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 1)
 k_tc_quad(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmBh, const QuadParams P) {
   extern __shared__ uint8_t smem_raw[];
-  constexpr int kAStat = TRI ? SCB_TRI_ASTAT : kAStatDef;
-  constexpr int kWBuf = TRI ? SCB_TRI_WBUF : kWBufDef;
-  constexpr int kPeerLag = TRI ? SCB_TRI_LAG : kPeerLagDef;
+  constexpr bool kLong = TRI || (SCB_QUAD_LONG_GROUPS && KCH > 8);
+  constexpr int kAStat = kLong ? SCB_TRI_ASTAT : kAStatDef;
+  constexpr int kWBuf = kLong ? SCB_TRI_WBUF : kWBufDef;
+  constexpr int kPeerLag = kLong ? SCB_TRI_LAG : kPeerLagDef;
   static_assert(kPeerLag % 2 == 1 && (kWBuf == 1 || kWBuf == 2), "peer lag must be odd; one or two landing buffers");
   constexpr uint32_t kNSB = TRI ? 1u : 2u;             // S buffers in TMEM
   constexpr uint32_t kColS0 = TRI ? 384u : 256u;       // TMEM: OUT [0, kColS0) | S buffers
@@ -1042,7 +1046,8 @@ int launch_quad_rows(const void* A, int64_t nA, const void* Bm, int64_t nB, int 
   // 512 < D <= 768: the single-S-buffer variant holds all 384 output columns of a pair in TMEM -- one launch, nothing
   // recomputed (tc_flags bit4; off = column groups, kept as the A/B reference).
   const bool tri = P.kch > 8 && P.kch <= 12 && (scb_tc_flags_get() & 16);
-  const int kAStat = tri ? SCB_TRI_ASTAT : kAStatDef, kWBuf = tri ? SCB_TRI_WBUF : kWBufDef;
+  const bool long_steps = tri || (SCB_QUAD_LONG_GROUPS && (P.kch == 12 || P.kch == 16));      // as the kernel's kLong
+  const int kAStat = long_steps ? SCB_TRI_ASTAT : kAStatDef, kWBuf = long_steps ? SCB_TRI_WBUF : kWBufDef;
   const int n_astat = P.kch < kAStat ? P.kch : kAStat;
   int nslots = (budget - (n_astat + 2 * kWBuf) * kSlotBytes) / kSlotBytes;
   nslots &= ~1;
