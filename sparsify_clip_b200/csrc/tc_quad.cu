@@ -865,7 +865,7 @@ int scb_make_tmap_2d_box(CUtensorMap* m, const void* base, int64_t rows, int D, 
 // is cut into (= output partial slots the caller must provide, "jparts").
 //
 // `align` (column operands that do not fit in L2, see scb_quad_align_spans): spans of WHOLE row blocks when that costs at
-// most 6 % of balance.  Equal spans start every cluster at a different column, so the clusters together touch the whole
+// most 6 % of balance (align == 2: whatever it costs).  Equal spans start every cluster at a different column, so the clusters together touch the whole
 // column operand all the time; whole-row-block spans make them walk the columns in step, and each tile then comes from
 // DRAM once and from L2 for everybody else (ncu at c4's shard, 8192 x 65536 x 768: 1.16 GB of DRAM reads per sweep for
 // a 100 MB operand, L2 hit rate 83 % against 98 % at c3).  It also leaves one partial slot per row block.
@@ -877,7 +877,7 @@ void scb_quad_span_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int align, i
   int64_t sp = (total + nc - 1) / nc;
   if (align && n_rp >= 1) {
     const int64_t rb_per = (n_rp + nc - 1) / nc;
-    if (rb_per * n_jb * 100 <= sp * 106) {
+    if (align == 2 || rb_per * n_jb * 100 <= sp * 106) {
       *n_used = (int)((n_rp + rb_per - 1) / rb_per);
       *span = rb_per * n_jb;
       *pmax = 1;
@@ -898,10 +898,11 @@ void scb_quad_span_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int align, i
 }
 
 // column operands beyond this size do not stay in the 126 MB L2 next to the row blocks and the partial outputs
-// (tc_flags bit5 forces it for any size: how the tests reach this plan with small inputs)
+// (tc_flags bit5 forces it for any size and any balance, = 2: how the tests reach this plan with small inputs)
 int scb_tc_flags_get();
 int scb_quad_align_spans(int64_t nB, int D) {
-  return ((scb_tc_flags_get() & 32) || (int64_t)nB * D * 2 > ((int64_t)64 << 20)) ? 1 : 0;
+  if (scb_tc_flags_get() & 32) return 2;
+  return (int64_t)nB * D * 2 > ((int64_t)64 << 20) ? 1 : 0;
 }
 
 namespace {

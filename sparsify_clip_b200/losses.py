@@ -412,11 +412,16 @@ class _FusedTermsFn(torch.autograd.Function):
                     # normalize((I + T) / 2); the result is the same array for both operands
                     gC = be.lunif_grad(core, C, u["coef"], u["dev_coef"])
                     cen = be.centroid_bwd(Ip, Tp, gC, c_inv, both=False)[0]
+        # d/dtau stays on the GPU here.  A temperature parameter that lives on the CPU (the reference's placement,
+        # sparsify_clip.py:716-717) needs a device-to-host copy of this scalar, i.e. a host synchronisation: it happens in
+        # backward AFTER the combine kernels are enqueued, so the device never waits for the host to come back from it
+        # (done here, it cost ~0.7 ms of idle GPU per step between the last sweep and the combine passes).
         dtau = None
+        ctx.tau_meta = None
         if need_tau and w_a != 0.0:
-            dt, tdev, shp = tau_t.dtype, tau_t.device, tau_t.shape
+            ctx.tau_meta = (tau_t.dtype, tau_t.device, tau_t.shape)
             s2 = scale * scale if sdev is None else sdev[0] * sdev[0]
-            dtau = (parts[NS] * (s2 * (-w_a / (2.0 * B)))).to(device=tdev, dtype=dt).reshape(shp)
+            dtau = parts[NS] * (s2 * (-w_a / (2.0 * B)))
         # The per-operand combine runs in backward with grad_output as its device-side scale: one pass writes the final
         # gradient in the input dtype (no separate multiply).  The sweep outputs stay alive until then.
         okdt = (torch.float32, torch.bfloat16, torch.float16)
@@ -442,7 +447,8 @@ class _FusedTermsFn(torch.autograd.Function):
             dT = be.grad_combine(Tp, Ip, ctx.out_dtypes[1], anchor=an_T, unif=un_T, l_coef=lc, dev_scale=g,
                                  extra=cen, e_coef=1.0).to(ctx.in_dtypes[1])
         if dtau0 is not None:
-            dtau = dtau0 * g.to(device=dtau0.device, dtype=dtau0.dtype)
+            dt, tdev, shp = ctx.tau_meta
+            dtau = (dtau0 * g.to(device=dtau0.device, dtype=dtau0.dtype)).to(device=tdev, dtype=dt).reshape(shp)
         return dI, dT, dtau, None, None, None, None, None, None, None, None
 
 

@@ -96,6 +96,18 @@ def test_c4_shard_exp10_vs_chunked_fp64_oracle():
     _check_config(8192, 768, 0.1, dict(anchor=1.0, align=alpha, unif_img=0.0, unif_txt=0.0, unif_cen=beta), True, 2048)
 
 
+def test_row_block_aligned_plan_at_shard_scale_vs_chunked_fp64_oracle():
+    """The work split c4 runs with (whole row blocks per cluster: its 100 MB column operand does not stay in L2), forced
+    here by tc_flags bit5 at B = 16384, D = 768: 64 row-block pairs over the clusters of 4, two per cluster."""
+    be = scb.get_backend()
+    prev = be.lib.scb_set_tc_flags(63)
+    try:
+        alpha, beta = scb.get_alpha(600, 1000, 50, 50), scb.get_beta(600, 1000, 20, 50)
+        _check_config(16384, 768, 0.1, dict(anchor=1.0, align=alpha, unif_img=0.5, unif_txt=0.0, unif_cen=beta), True, 2048)
+    finally:
+        be.lib.scb_set_tc_flags(prev)
+
+
 def test_c2_exp4_vs_chunked_fp64_oracle():
     """BASELINE c2: exp 4 (anchor + lalign + lunif(centroids)), B = 4096, D = 512."""
     _check_config(4096, 512, 0.1, dict(anchor=1.0, align=1.0, unif_img=0.0, unif_txt=0.0, unif_cen=1.0), False, 4096)
