@@ -15,6 +15,8 @@ D2H read of the loss inside the timed region); `roofline.frac` = algorithmic FLO
 (ms_per_step x measured bf16 peak), with the sweep-only and dominant-kernel figures under their own
 keys; `cpu_baseline` = the torch port of the reference op sequence (oracle/torch_port.py) on the host
 cores, on a bounded B = 8192 sample (measured sample time printed, `value` extrapolated and marked);
+`eager_gpu_baseline` = the same port run as eager PyTorch on THIS GPU at B = 4096 (the largest size torch.pdist's
+backward fits), with this library on the same sample next to it (SURVEY.md §8d's second comparison);
 `parity` (N > 1, untimed) = sharded result vs the same kernels unsharded and vs the fp64 closed form.
 `--config c2|c3|c4` selects another BASELINE.json workload.  `--impl reference` times the CPU path alone.
 """
@@ -81,10 +83,19 @@ def parse():
 TRAFFIC_FILES = ("r02_traffic.json", "r01_traffic.json")
 
 
-def measured_traffic():
+def measured_traffic(config="c3", world=1):
     """(DRAM bytes per launch of the dominant kernel, provenance) from the newest committed ncu --set full capture under
-    profiles/ -- a number read from a file, NOT measured in this run -- or (None, why)."""
-    for name in TRAFFIC_FILES:
+    profiles/ -- a number read from a file, NOT measured in this run -- or (None, why).  The captures are of fixed shapes:
+    c3's sweeps on one GPU, and c4's 8-GPU shard (8192 rows x 65536 columns, D = 768); other runs carry null."""
+    if config == "c4":
+        if world != 8:
+            return None, "no ncu capture of this shape (profiles/r03_traffic_c4_shard.json is c4's 8-GPU shard)"
+        files = ("r03_traffic_c4_shard.json",)
+    elif config == "c3" and world == 1:
+        files = TRAFFIC_FILES
+    else:
+        return None, "no ncu capture of this shape (the committed captures are c3 on one GPU and c4's 8-GPU shard)"
+    for name in files:
         p = os.path.join(ROOT, "profiles", name)
         try:
             with open(p) as f:
@@ -103,6 +114,15 @@ def peaks():
             d = json.load(f)
         return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
     return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+def sustained_peak():
+    """MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS back to back for 4 s), or None."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"])
+    except Exception:
+        return None
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -195,6 +215,56 @@ def cpu_baseline_record(args, steps=2, warmup=1):
             "sample": f"oracle/torch_port.py {args.cfg['name']} fwd+bwd fp32 at B={r['bs']}, D={args.dim}: median {r['t']:.3f} s/step "
                       f"over {steps} steps = {r['sample_value']:.1f} pairs/s MEASURED"
                       + (f"; value extrapolated to B={args.batch} by (B/{r['bs']})^2 (pairs/s falls as 1/B)" if r["extrapolated"] else "")}
+
+
+def eager_gpu_baseline_record(args, scb, torch, dev, steps=5, warmup=2):
+    """Part of the baseline leg ("also time the reference's eager GPU path on one B200 where it fits"): the
+    torch port of the reference op sequence run on THIS GPU, fp32 without autocast (the parity target of SURVEY.md §A.3),
+    on a bounded sample -- torch.pdist's backward keeps B(B-1)/2 x D fp32 of scratch (17 GB at B = 4096, D = 512; 68 GB at
+    B = 8192), so B = 4096 is the largest size that always fits.  Next to it: this library on the same sample (bf16,
+    eager launches), timed the same way.  Reported, never the target; untimed with respect to the bench line."""
+    from oracle import torch_port
+    bs = min(4096, args.batch)
+    w = _weights_tuple(args.cfg["w"])
+    g = torch.Generator(device=dev).manual_seed(42)
+    I = torch.nn.functional.normalize(torch.randn(bs, args.dim, generator=g, device=dev), dim=-1)
+    T = torch.nn.functional.normalize(I + 0.5 * torch.randn(bs, args.dim, generator=g, device=dev), dim=-1)
+
+    def timed(fn):
+        ts = []
+        for i in range(warmup + steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    try:
+        tau = torch.tensor(TAU, device=dev) if args.cfg["learn_tau"] else TAU
+        torch.cuda.reset_peak_memory_stats(dev)
+        base = torch.cuda.memory_allocated(dev)
+        ms_ref = timed(lambda: torch_port.fwd_bwd(I, T, tau, w))
+        ref_mem = torch.cuda.max_memory_allocated(dev) - base
+        Ib, Tb = I.to(torch.bfloat16).requires_grad_(True), T.to(torch.bfloat16).requires_grad_(True)
+        tp = torch.nn.Parameter(torch.tensor(TAU)) if args.cfg["learn_tau"] else TAU
+
+        def ours():
+            Ib.grad = Tb.grad = None
+            scb.weighted_loss(Ib, Tb, tp, args.cfg["w"]).backward()
+        ms_ours = timed(ours)
+    except Exception as exc:
+        torch.cuda.empty_cache()
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+    torch.cuda.empty_cache()
+    return {"value": bs / (ms_ref * 1e-3), "unit": UNIT, "kind": "port", "device": torch.cuda.get_device_name(dev),
+            "ms_per_step": ms_ref, "peak_scratch_bytes": int(ref_mem),
+            "ours_same_sample": {"value": bs / (ms_ours * 1e-3), "ms_per_step": ms_ours, "launch": "eager launches, bf16"},
+            "sample": f"oracle/torch_port.py {args.cfg['name']} fwd+bwd, fp32 eager PyTorch on the GPU (mm + cross_entropy, "
+                      f"pdist and its backward, as the reference runs them), B={bs}, D={args.dim}: median of {steps} steps after "
+                      f"{warmup} warm-ups, CUDA events; larger B does not fit torch.pdist's backward scratch"}
 
 
 def run_reference(args):
@@ -490,6 +560,7 @@ def run_ours(args):
     pass_ms = pm.item()
     flops_alg = 2.0 * cfg["contractions"] * B * B * D   # anchor 3 contractions, each lunif 2 (2 B^2 D each)
     peak, peak_src = peaks()
+    peak_sust = sustained_peak()
     achieved = flops_alg / world / (pass_ms * 1e-3) / 1e12      # per-GPU TFLOP/s of the B x B passes
 
     # ---- end to end through the public API from pinned host memory
@@ -587,7 +658,7 @@ def run_ours(args):
 
     if rank == 0:
         whole = flops_alg / world / (ms_per_step * 1e-3) / 1e12        # per-GPU algorithmic TFLOP/s over the WHOLE step
-        traffic, traffic_src = measured_traffic()
+        traffic, traffic_src = measured_traffic(args.config, world)
         dom = max(per, key=lambda k: sum(per[k])) if per else None
         dom_calls = {"lse": 1.0, "anchor_grad": 2.0, "lunif": 2.0}      # algorithmic contractions one launch of each covers
         dom_ms = (sum(per[dom]) / len(per[dom])) if dom else None
@@ -620,6 +691,8 @@ def run_ours(args):
             # `frac` is the WHOLE-STEP fraction: algorithmic FLOPs of the step / (ms_per_step x peak), i.e. it follows from
             # `ms_per_step` above.  The sweep-only and dominant-kernel figures explain it and sit under their own keys.
             "roofline": {"bound": "tensor", "achieved": whole, "peak": peak, "unit": "TFLOP/s", "frac": whole / peak,
+                         "frac_vs_sustained_peak": (whole / peak_sust) if peak_sust else None,      # back-to-back cuBLAS, 4 s
+                         "frac_vs_datasheet_2250": whole / 2250.0,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_flops_per_step": flops_alg,
                          "sweeps_only": {"ms_per_step": pass_ms, "achieved": achieved, "frac": achieved / peak,
@@ -635,6 +708,7 @@ def run_ours(args):
             line["parity"] = parity
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_record(args)
+            line["eager_gpu_baseline"] = eager_gpu_baseline_record(args, scb, torch, dev)
         print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
