@@ -20,6 +20,8 @@
 // TMEM columns: OUT [0,256) | S0 [256,384) | S1 [384,512).
 //
 // Column-tail / row-tail / D-tail handling relies on TMA zero fill plus masks in the epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -46,7 +48,8 @@ constexpr float kColBias = 100.f;          // M_LSE2: exponent bias of the per-b
 struct TcParams {
   int64_t nA, nB;
   int D, kch, nsplit, n_rb, n_jb, jparts;
-  int a_stationary, nstage, g_in_tmem, fmt;  // fmt: 1 bf16, 0 fp16 (both MMA operands must share it:
+  int a_stationary, nstage, g_in_tmem, fmt;  // a_stationary: K-chunks of the row block resident in shared memory (kch = all,
+                                             // 0 = none, else even).  fmt: 1 bf16, 0 fp16 (both MMA operands must share it:
                                              // a mixed-format kind::f16 descriptor is an illegal instruction)
   float p0;                                  // LSE/anchor: scale*log2e ; lunif: t*log2e
   const float* p0_dev;                       // optional device multiplier of p0 (1/tau of a device-resident temperature)
@@ -102,12 +105,14 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   extern __shared__ uint8_t smem_raw[];
   const float p0_eff = P.p0_dev ? P.p0 * __ldg(P.p0_dev) : P.p0;
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t a_bytes = P.a_stationary ? (uint32_t)P.kch * kSlotBytes : 0u;
+  // resident K-chunks of the row block: all of them (D <= 512), or the first n_as (even) while the rest streams with the
+  // column tiles (D > 512: a 128 x 768 row block is 192 KB), or none
+  const int n_as = KCH ? KCH : P.a_stationary;
+  const uint32_t a_bytes = (uint32_t)n_as * kSlotBytes;
   const uint32_t sm_a = smem_base;
   const uint32_t sm_ring = sm_a + a_bytes;
   const uint32_t sm_g = sm_ring + (uint32_t)P.nstage * kPairBytes;
   const int kch = KCH ? KCH : P.kch;
-  const bool a_stat = KCH ? true : (P.a_stationary != 0);   // compile-time in the specialised kernels
   const uint32_t nps = (uint32_t)P.nstage;
   const uint32_t g_bytes = (GRAD && !P.g_in_tmem) ? 2u * kSlotBytes : 0u;
   const uint32_t sm_cbuf = sm_g + g_bytes;            // 2 x 128 floats
@@ -160,12 +165,12 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
       const int nt = jb_hi - jb_lo;
       const int gch = min(4, kch - 4 * split);
-      if (a_stat) {
+      if (n_as > 0) {
         ptx::mbar_wait(bar(BAR_A_EMPTY), a_empty_par, 100);
         a_empty_par ^= 1;
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(bar(BAR_A_FULL), (uint32_t)kch * kSlotBytes);
-          for (int kc = 0; kc < kch; ++kc) ptx::tma_load_2d(sm_a + kc * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_A_FULL));
+          ptx::mbar_expect_tx(bar(BAR_A_FULL), (uint32_t)n_as * kSlotBytes);
+          for (int kc = 0; kc < n_as; ++kc) ptx::tma_load_2d(sm_a + kc * kSlotBytes, &tmA, kc * 64, rb * 128, bar(BAR_A_FULL));
         }
         __syncwarp();
       }
@@ -186,7 +191,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       };
       for (int t = 0; t < nt; ++t) {
         for (int kc = 0; kc < kch; kc += 2) {
-          if (!a_stat) load_pair(&tmA, kc * 64, rb * 128, min(2, kch - kc), 120);
+          if (kc >= n_as) load_pair(&tmA, kc * 64, rb * 128, min(2, kch - kc), 120);
           load_pair(&tmB, kc * 64, (jb_lo + t) * 128, min(2, kch - kc), 121);
         }
         if (GRAD && t >= 1) load_v(t - 1);
@@ -213,7 +218,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int jb_lo = (int)((int64_t)P.n_jb * jp / P.jparts), jb_hi = (int)((int64_t)P.n_jb * (jp + 1) / P.jparts);
       const int nt = jb_hi - jb_lo;
       const int gch = min(4, kch - 4 * split);
-      if (a_stat) {
+      if (n_as > 0) {
         ptx::mbar_wait(bar(BAR_A_FULL), a_full_par, 200);
         a_full_par ^= 1;
       }
@@ -223,7 +228,8 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t d_tmem = tmem_base + kColS0 + 128u * b;
         auto kgroup = [&](int kc, int nk) {      // 8 MMAs (two 64-wide K chunks) behind one full-barrier wait
           uint32_t alo, sa = 0;
-          if (a_stat) {
+          const bool a_res = kc < n_as;
+          if (a_res) {
             alo = a_lo0 + (uint32_t)kc * kChunkLo;
           } else {
             sa = ring.take(nps);
@@ -244,7 +250,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                idesc1, (uint32_t)((kc | (int)i | (int)k) != 0));
               }
             }
-            if (!a_stat) ptx::umma_commit(bar(BAR_EMPTY + sa));
+            if (!a_res) ptx::umma_commit(bar(BAR_EMPTY + sa));
             ptx::umma_commit(bar(BAR_EMPTY + sb));
           }
           __syncwarp();
@@ -258,7 +264,7 @@ k_tc_pass(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         if (ptx::elect_one()) {
           ptx::umma_commit(bar(BAR_S_FULL + b));
-          if (last && a_stat) ptx::umma_commit(bar(BAR_A_EMPTY));
+          if (last && n_as > 0) ptx::umma_commit(bar(BAR_A_EMPTY));
         }
         __syncwarp();
         ++gt1;
@@ -600,6 +606,26 @@ std::atomic<int> g_tc_flags{31};   // bit0: weight tile in TMEM (TS-mode MMA2) -
                       //       in TMEM, nothing recomputed) instead of two column-group launches
                       // bit5: (tests) the cluster-of-4 kernel's row-block-aligned span plan for any operand size
 
+// Measured (profiles/r03q_lse_residency.log, one-sweep LSE at 32768^2 x 768 / 8192 x 65536 x 768 / 16384^2 x 1024):
+// 0 resident 919 / 1009 / 824 TFLOP/s, 4: 915 / 1004 / 824, 6: 910 / 983 / 809, 8: 829 / 880 / 676 -- what these sweeps
+// pull from L2 is NOT what bounds them (the single-CTA SS MMA reads all of an SM's shared-memory bandwidth); the deeper
+// ring wins.  Default: none resident.
+#ifndef SCB_PASS_ASTAT_BIG
+#define SCB_PASS_ASTAT_BIG 0
+#endif
+// resident row-block chunks of the non-gradient sweeps when D > 512 (even; SCB_PASS_ASTAT in the environment overrides
+// the compiled default -- a tuning knob, read once)
+int pass_astat_big() {
+  static const int v = [] {
+    const char* e = getenv("SCB_PASS_ASTAT");
+    int n = e ? atoi(e) : SCB_PASS_ASTAT_BIG;
+    if (n < 0) n = 0;
+    if (n > 8) n = 8;
+    return n & ~1;
+  }();
+  return v;
+}
+
 template <int MODE>
 int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int64_t ldA, int64_t ldB, int dtype,
               TcParams P, cudaStream_t s) {
@@ -617,9 +643,12 @@ int launch_tc(const void* A, int64_t nA, const void* Bm, int64_t nB, int D, int6
   SCB_CHECK_ARG(P.jparts >= 1 && P.jparts <= P.n_jb, SCB_E_ARG, "jparts=%d outside [1, %d]", P.jparts, P.n_jb);
   P.fmt = (dtype == SCB_BF16) ? 1 : 0;
   P.g_in_tmem = (GRAD && (g_tc_flags & 1)) ? 1 : 0;
-  P.a_stationary = (P.kch <= 8) ? 1 : 0;
+  // Resident K-chunks of the row block.  D <= 512: all.  D > 512 (a 128 x 768 row block is 192 KB): the first
+  // pass_astat_big() may stay while the rest streams with every column tile (fewer bytes from L2, shallower ring) --
+  // measured not to pay, see SCB_PASS_ASTAT_BIG.  The gradient modes (only D > 1024 still runs them here) stream everything.
+  P.a_stationary = (P.kch <= 8) ? P.kch : (GRAD ? 0 : pass_astat_big());
   const int budget = 232448 - 1024 /*align slack*/ - 1024 /*cbuf*/ - 1024 /*barriers*/ ;
-  const int fixed = (P.a_stationary ? P.kch * kSlotBytes : 0) + ((GRAD && !P.g_in_tmem) ? 2 * kSlotBytes : 0);
+  const int fixed = P.a_stationary * kSlotBytes + ((GRAD && !P.g_in_tmem) ? 2 * kSlotBytes : 0);
   int nstage = (budget - fixed) / kPairBytes;      // pair-slots of 32 KB
   if (nstage > kMaxStages) nstage = kMaxStages;
   SCB_CHECK_ARG(nstage >= 2, SCB_E_SHAPE, "not enough shared memory for the tile ring (D=%d)", D);
