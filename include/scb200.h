@@ -72,6 +72,12 @@ int scb_pass_plan(int path, int64_t nA, int64_t nB, int D, int grad, int n_sm, i
  * whatever the operand size (by default only when the column operand exceeds 64 MB, i.e. does not stay in L2).
  * Default: bits 0-4 set.  Returns the previous value. */
 int scb_set_tc_flags(int flags);
+/* Work split of the cluster-of-4 gradient kernel (host-only arithmetic, no CUDA call): the (256-row block, 128-column
+ * tile) space of n_rp x n_jb items, linearised row-block-major, is cut into *n_used contiguous spans of *span items, one
+ * per cluster; *pmax = the largest number of spans that touch one row block (= output partial slots).  align != 0: spans
+ * of whole row blocks when that costs at most 6 % of balance (2: whatever it costs) -- the split used when the column
+ * operand does not stay in L2. */
+int scb_quad_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int align, int* n_used, int64_t* span, int* pmax);
 /* Which kernel a TC gradient pass over nA rows of width D runs on the current device:
  * 0 = single CTA (k_tc_pass), 1 = CTA pair (k_tc_pair), 2 = cluster of 4 (k_tc_quad).  In *units (may be
  * null): how many of those run concurrently (SMs, pairs, clusters).  The first call on a device asks the

@@ -22,6 +22,8 @@ SIGNATURES = {
     "scb_pass_plan": [_i32, _i64, _i64, _i32, _i32, _i32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)],
     "scb_set_tc_flags": [_i32],
     "scb_grad_kernel_kind": [_i64, _i32, _i32, ctypes.POINTER(ctypes.c_int)],
+    "scb_quad_plan": [_i64, _i64, _i32, _i32, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64),
+                      ctypes.POINTER(ctypes.c_int)],
     "scb_row_sqnorm": [_vp, _i64, _i32, _i64, _i32, _vp, _vp],
     "scb_row_dot": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _vp],
     "scb_lalign_rows": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _vp],

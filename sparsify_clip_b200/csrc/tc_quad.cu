@@ -897,6 +897,13 @@ void scb_quad_span_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int align, i
   *pmax = mx;
 }
 
+// the same plan through the C ABI (host-only arithmetic; what the tests walk against their mirror of the kernel's loop)
+extern "C" int scb_quad_plan(int64_t n_rp, int64_t n_jb, int n_clusters, int align, int* n_used, int64_t* span, int* pmax) {
+  SCB_CHECK_ARG(n_rp >= 1 && n_jb >= 1 && n_clusters >= 1 && n_used && span && pmax, SCB_E_ARG, "quad_plan: bad argument");
+  scb_quad_span_plan(n_rp, n_jb, n_clusters, align, n_used, span, pmax);
+  return 0;
+}
+
 // column operands beyond this size do not stay in the 126 MB L2 next to the row blocks and the partial outputs
 // (tc_flags bit5 forces it for any size and any balance, = 2: how the tests reach this plan with small inputs)
 int scb_tc_flags_get();

@@ -92,6 +92,13 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert b"anchor" in lib.scb_last_error()
     assert lib.scb_grad_combine(p, p, 4, 8, 8, 8, _lib.SCB_BF16, None, 0, None, None, None, 1.0, 1.0, None, 0, None, 0, 0.0,
                                 None, 1.0, None, 0.0, None, p, _lib.SCB_BF16, 4, None, None) == -1
+    # the SM push of the peer gather: 16-byte granularity of the shard and of every pointer; the plan helper's arguments
+    dst = (ctypes.c_void_p * 2)(p, p)
+    assert lib.scb_peer_push_sm(p, 24, dst, 2, f, p, 2, f, None) == -1 and b"16-byte" in lib.scb_last_error()
+    assert lib.scb_peer_push_sm(p, 32, dst, 0, f, p, 2, f, None) == -1
+    assert lib.scb_peer_push_sm(None, 32, dst, 2, f, p, 2, f, None) == -1
+    n_used, span, pmax = ctypes.c_int(0), ctypes.c_int64(0), ctypes.c_int(0)
+    assert lib.scb_quad_plan(0, 4, 33, 0, ctypes.byref(n_used), ctypes.byref(span), ctypes.byref(pmax)) == -1
 
 
 def test_no_cpu_fallback():
@@ -316,3 +323,56 @@ def test_pair_span_walk_covers_every_tile_once():
             slots[rb].append(jp)
         assert all(v == 1 for row in seen for v in row), (n_rb, n_jb, n_sm)
         assert all(s == list(range(len(s))) for s in slots), (n_rb, n_jb, n_sm)
+
+
+def _quad_plan(n_rp, n_jb, n_cl, align):
+    n_used, span, pmax = ctypes.c_int(0), ctypes.c_int64(0), ctypes.c_int(0)
+    assert _lib.load().scb_quad_plan(n_rp, n_jb, n_cl, align, ctypes.byref(n_used), ctypes.byref(span), ctypes.byref(pmax)) == 0
+    return n_used.value, span.value, pmax.value
+
+
+def test_quad_span_walk_covers_every_tile_once():
+    """Host mirror of the cluster-of-4 kernel's span walk (csrc/tc_quad.cu: SCB_QUAD_FOR_SEGMENTS / SCB_QUAD_ITEM_SETUP)
+    over the C planner's output, for the equal-span split and for the row-block-aligned one (BASELINE c4's shapes
+    included): every (256-row block, tile) in exactly one segment, partial slots of a row block 0 .. k-1 with k <= pmax,
+    both pairs of a cluster own tiles in every segment of two or more tiles, aligned spans are whole row blocks."""
+    import random
+    rng = random.Random(11)
+    shapes = [(128, 256, 33), (32, 512, 33), (256, 512, 33), (16, 256, 33), (1, 1, 33), (3, 7, 33), (120, 256, 33), (64, 128, 33)]
+    shapes += [(rng.randint(1, 300), rng.randint(1, 600), rng.choice([1, 4, 33, 36])) for _ in range(80)]
+    for n_rp, n_jb, n_cl in shapes:
+        for align in (0, 1, 2):
+            n_used, span, pmax = _quad_plan(n_rp, n_jb, n_cl, align)
+            total = n_rp * n_jb
+            assert 1 <= n_used <= n_cl and n_used * span >= total and (n_used - 1) * span < total, (n_rp, n_jb, n_cl, align)
+            assert 1 <= pmax <= 16
+            if align == 2:
+                assert span % n_jb == 0 and pmax == 1
+            if align == 1:       # accepted only within 6 % of the balanced span
+                eq = _quad_plan(n_rp, n_jb, n_cl, 0)
+                assert (span % n_jb == 0 and pmax == 1 and span * 100 <= max(eq[1], -(-total // min(n_cl, total))) * 106) or \
+                    (n_used, span, pmax) == eq
+            seen = [[0] * n_jb for _ in range(n_rp)]
+            slots = [[] for _ in range(n_rp)]
+            for cl in range(n_used):
+                g, g_end, item = cl * span, min(cl * span + span, total), 0
+                while g < g_end:
+                    rp = g // n_jb
+                    jb_lo = g - rp * n_jb
+                    nt = min(n_jb - jb_lo, g_end - g)
+                    jp = cl - (rp * n_jb) // span
+                    own = [(nt - t_first + 1) // 2 if nt > t_first else 0 for t_first in ((0 ^ (item & 1)) & 1, (1 ^ (item & 1)) & 1)]
+                    assert sum(own) == nt and (nt < 2 or min(own) >= 1)
+                    assert 0 <= jp < pmax, (n_rp, n_jb, n_cl, align, cl, rp, jp, pmax)
+                    for j in range(jb_lo, jb_lo + nt):
+                        seen[rp][j] += 1
+                    slots[rp].append(jp)
+                    g += nt
+                    item += 1
+            assert all(v == 1 for row in seen for v in row), (n_rp, n_jb, n_cl, align)
+            assert all(s_ == list(range(len(s_))) for s_ in slots), (n_rp, n_jb, n_cl, align)
+    # BASELINE c4: the 8-GPU shard (32 row-block pairs x 512 tiles) runs 32 clusters of one row block each, the single
+    # GPU (256 x 512) 32 clusters of 8; c3's 120 x 256 (row split) stays on equal spans (aligned would cost 10 %)
+    assert _quad_plan(32, 512, 33, 1) == (32, 512, 1)
+    assert _quad_plan(256, 512, 33, 1) == (32, 8 * 512, 1)
+    assert _quad_plan(120, 256, 33, 1) == _quad_plan(120, 256, 33, 0)
