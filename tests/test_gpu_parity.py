@@ -156,7 +156,7 @@ def test_row_block_aligned_spans_of_the_cluster_kernel(B, D, tau):
     be = scb.get_backend()
     w = dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.5, unif_cen=0.0)
     got = {}
-    for flags in (31, 63):
+    for flags in (31, 63, 15):       # 15: D = 768 in two column groups instead of the single-S-buffer variant (bit4 off)
         prev = be.lib.scb_set_tc_flags(flags)
         prev_mode = scb.set_fp32_mode("bf16")
         try:
