@@ -1,5 +1,5 @@
 """One optimisation step of the reference training loop (sparsify_clip.py:750-965) with the loss path replaced by
-sparsify_clip_b200: encode -> pre-loss normalise (:772-773) -> loss_type ladder (:775-938) -> backward ->
+sparsify_clip_b200: encode -> [pre-loss normalise (:772-773) -> loss_type ladder (:775-938)] as ONE node -> backward ->
 AdamW (:730) -> LR schedule (:68-107, :735-737).
 
 Sharded use (one process per GPU): the encoders are wrapped in DistributedDataParallel by the caller, `group` is
@@ -38,8 +38,11 @@ class TrainStep:
     config: the reference's YAML keys (loss_type, only_lunif_epochs, anchor_temperature, anchor_temperature_learnable,
     learning_rate, fp16, the beta/alpha schedule keys)."""
 
-    def __init__(self, model, config, t_total, *, group=None, amp_dtype=None, steps_sparsify=462):
+    def __init__(self, model, config, t_total, *, group=None, amp_dtype=None, steps_sparsify=462, fuse_normalize=True):
         self.model, self.config, self.t_total, self.group = model, config, int(t_total), group
+        # the pre-loss normalise (:772-773) inside the loss node: its backward rides on the node's gradient combine pass and
+        # the encoders receive d loss / d (raw embedding) directly; False = a separate l2_normalize node in front
+        self.fuse_normalize = bool(fuse_normalize)
         self.world = dist.get_world_size(group) if group is not None else 1
         self.temperature = config["anchor_temperature"]
         params = list(model.parameters())
@@ -63,11 +66,13 @@ class TrainStep:
             img, txt = m.encode_image(images), m.encode_text(tokens)
         else:                           # DDP wrapper: one forward so that its reducer sees one backward
             img, txt = m(images, tokens)
+        if self.fuse_normalize:
+            return img, txt                 # raw encoder outputs: loss() normalises them
         return scb.l2_normalize(img), scb.l2_normalize(txt)
 
     def loss(self, img, txt, epoch):
         return scb.compose_loss(self.config, img, txt, self.temperature, epoch=epoch, current_batch=self.current_batch,
-                                t_total=self.t_total, group=self.group)
+                                t_total=self.t_total, group=self.group, normalize=self.fuse_normalize)
 
     def __call__(self, images, tokens, epoch=0):
         self.current_batch += 1

@@ -50,7 +50,7 @@ extern "C" {
 
 /* ABI revision of this header.  scb_version() returns the revision the loaded library was BUILT against; a binding
  * must refuse a library whose revision differs (argument lists may have changed). */
-#define SCB_ABI_VERSION 202
+#define SCB_ABI_VERSION 203
 int scb_version(void);
 /* Device-resident temperature.  Every entry that takes the logit scale 1/tau as a host float (`scale`, and the
  * coefficients derived from it) also takes `const float* scale_dev` as its last argument before the stream: when non-NULL
@@ -206,13 +206,20 @@ int scb_lunif_grad_finalize(const float* U, int jparts, const float* rq, int npa
  * gs = dev_scale ? *dev_scale : 1;  uc = u_coef * (u_dev_coef ? *u_dev_coef : 1).  a_out / u_out / extra may be NULL
  * (term absent); l_coef == 0 skips L_align.  X = the operand's rows, Y = the paired rows of the other modality;
  * extra = a finished contiguous fp32 [n, D] gradient term (the centroid chain of sparsify_clip.py:353/804: L_unif of
- * the normalised centroids pulled back through the normalisation by scb_centroid_bwd). */
+ * the normalised centroids pulled back through the normalisation by scb_centroid_bwd).
+ * unit_src / unit_inv (both or neither): the pre-loss normalise of sparsify_clip.py:772-773 fused in.  X then holds the
+ * NORMALISED rows E_i / ||E_i|| the loss was evaluated on, unit_src the un-normalised rows E (dtype unit_dtype, row stride
+ * ld_unit), unit_inv[i] = 1 / ||E_i|| (scb_normalize_fwd), and the pass writes the gradient w.r.t. E:
+ *   dE[i,:] = ( dX[i,:] - e_i (e_i . dX[i,:]) ) * unit_inv[i],   e_i = E_i * unit_inv[i] in fp32
+ * i.e. scb_normalize_bwd applied to the fp32 dX before the output conversion.  Needs D <= 2048 (16-byte aligned rows, D % 8
+ * == 0) or D <= 256 otherwise: a row is reduced inside one thread block. */
 int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, int64_t ldX, int64_t ldY, int dtype,
                      const float* a_out, int a_jparts, const float* row_lse, const float* col_lse_rows,
                      const float* diag, float scale, float a_coef, const float* u_out, int u_jparts,
                      const float* rq, int rq_parts, float u_coef, const float* u_dev_coef, float l_coef,
                      const float* extra, float e_coef, const float* dev_scale, void* dX, int out_dtype,
-                     int64_t ldOut, const float* scale_dev, void* stream);
+                     int64_t ldOut, const float* scale_dev, const void* unit_src, int64_t ld_unit, int unit_dtype,
+                     const float* unit_inv, void* stream);
 
 /* Scalar assembly of the composed loss (the additions of the ladder, sparsify_clip.py:778-938, on the partial sums):
  * parts = [sum_i row_lse, sum_j col_lse, sum_i I_i.T_i, sum_i |I_i - T_i|^2, rs(img), rs(txt), rs(cen)] (device),

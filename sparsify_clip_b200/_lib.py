@@ -50,7 +50,7 @@ SIGNATURES = {
     "scb_loss_assemble": [_vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp],
     "scb_lse2_fold_ranks": [_vp, _i32, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp],
     "scb_grad_combine": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _f32, _f32, _vp, _i32, _vp, _i32,
-                         _f32, _vp, _f32, _vp, _f32, _vp, _vp, _i32, _i64, _vp, _vp],
+                         _f32, _vp, _f32, _vp, _f32, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i32, _vp, _vp],
     "scb_sparsify_sum_pass": [_vp, _i64, _vp, _i64, _i32, _i64, _i64, _i32, _i64, _i32, _vp, _i32, _vp],
     "scb_col_sum": [_vp, _vp, _i64, _i32, _i64, _i64, _i32, _f32, _vp, _i32, _vp, _vp],
     "scb_gram_dd": [_vp, _i64, _i32, _i64, _i32, _vp, _f32, _vp, _i32, _vp, _vp],

@@ -431,10 +431,24 @@ class CudaBackend:
         self._count()
         return {"out": out, "jparts": jp, "ws": self.sum(ws) if want_ws else None}
 
-    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None, extra=None, e_coef=0.0):
+    @staticmethod
+    def can_fuse_normalize(X, E):
+        """Whether grad_combine can apply the backward of the pre-loss normalise itself (a row is reduced inside one
+        thread block: D <= 2048 with 16-byte aligned rows, see scb_grad_combine)."""
+        D = X.shape[1]
+        if E.stride(1) != 1 or E.dtype not in _DT:
+            return False
+        vec = (D % 8 == 0 and X.stride(0) % 8 == 0 and E.stride(0) % 8 == 0 and X.data_ptr() % 16 == 0
+               and E.data_ptr() % 16 == 0)
+        return D <= 256 or (vec and D <= 2048)
+
+    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None, extra=None, e_coef=0.0,
+                     unit=None):
         """dX = a_coef (sum_p out[p] + dcoef Y) + u_coef (rq X - sum_p U[p]) + l_coef (X - Y) + e_coef extra, one
         streaming pass.  anchor = dict(out, jparts, row_lse, col_lse_rows, diag, scale, coef);
-        unif = dict(core, coef, dev_coef); extra = contiguous fp32 [n, D]."""
+        unif = dict(core, coef, dev_coef); extra = contiguous fp32 [n, D].
+        unit = (E, inv): X is normalize(E) with inv = 1 / ||E_i||; the pass then returns the gradient w.r.t. E (the
+        backward of sparsify_clip.py:772-773 fused in; check can_fuse_normalize first)."""
         if extra is not None:
             assert extra.dtype == torch.float32 and extra.is_contiguous() and extra.shape == X.shape
         n, D = X.shape
@@ -448,7 +462,9 @@ class CudaBackend:
                 _ptr(a.get("diag")), float(a.get("scale", 0.0)), float(a.get("coef", 0.0)),
                 _ptr(core.get("U")), int(core.get("jparts", 0)), _ptr(core.get("rq")), int(core.get("nparts", 0)),
                 float(u.get("coef", 0.0)), _ptr(u.get("dev_coef")), float(l_coef), _ptr(extra), float(e_coef),
-                _ptr(dev_scale), _ptr(dX), _DT[out_dtype], dX.stride(0), _ptr(a.get("scale_dev")), self._stream()),
+                _ptr(dev_scale), _ptr(dX), _DT[out_dtype], dX.stride(0), _ptr(a.get("scale_dev")),
+                _ptr(unit[0]) if unit else None, unit[0].stride(0) if unit else 0, _DT[unit[0].dtype] if unit else 0,
+                _ptr(unit[1]) if unit else None, self._stream()),
                 "grad_combine")
         self._count()
         return dX

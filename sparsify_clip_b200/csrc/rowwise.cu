@@ -434,17 +434,16 @@ struct CombineArgs {
   const float* dev_scale;
   void* dX; int out_dtype; int64_t ldOut;
   const float* scale_dev;      // optional device multiplier of `scale` and `a_coef` (1/tau of a device-resident temperature)
+  // optional pull-back through the pre-loss normalise X = E / ||E|| (sparsify_clip.py:772-773): the un-normalised rows
+  // and their 1 / ||E||; the kernel then writes dE = (g - e (e . g)) / ||E|| with e = E / ||E|| in fp32
+  const void* unit_src; int64_t ld_unit; int unit_dtype; const float* unit_inv;
 };
 
+// every term of `row`, columns [d, d + W): g before the output conversion (everything of the combine but the store)
 template <bool VEC>
-__global__ void __launch_bounds__(256) k_grad_combine(const CombineArgs a) {
+__device__ __forceinline__ void combine_terms(const CombineArgs& a, int64_t row, int d, float (&g)[8]) {
   constexpr int W = VEC ? 8 : 1;
-  const int per_row = (a.D + W - 1) / W;
-  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const int64_t row = idx / per_row;
-  if (row >= a.n) return;
-  const int d = (int)(idx - row * per_row) * W;
-  float x[8], y[8], g[8];
+  float x[8], y[8];
   const bool need_y = (a.a_out != nullptr) || (a.l_coef != 0.f);
   if (VEC) {
     scb_ld8(a.X, a.dtype, row * a.ldX + d, x);
@@ -513,6 +512,10 @@ __global__ void __launch_bounds__(256) k_grad_combine(const CombineArgs a) {
 #pragma unroll
     for (int i = 0; i < W; ++i) g[i] *= gs;
   }
+}
+
+template <bool VEC>
+__device__ __forceinline__ void combine_store(const CombineArgs& a, int64_t row, int d, const float (&g)[8]) {
   const int64_t oo = row * a.ldOut + d;
   if (VEC) {
     if (a.out_dtype == SCB_F32) {
@@ -537,6 +540,58 @@ __global__ void __launch_bounds__(256) k_grad_combine(const CombineArgs a) {
   } else {
     scb_st(a.dX, a.out_dtype, oo, g[0]);
   }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_grad_combine(const CombineArgs a) {
+  constexpr int W = VEC ? 8 : 1;
+  const int per_row = (a.D + W - 1) / W;
+  const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t row = idx / per_row;
+  if (row >= a.n) return;
+  const int d = (int)(idx - row * per_row) * W;
+  float g[8];
+  combine_terms<VEC>(a, row, d, g);
+  combine_store<VEC>(a, row, d, g);
+}
+
+// The same pass with the backward of the pre-loss normalise fused in: a row is owned by `tpr` consecutive threads (whole
+// warps) of one block, so that e . g is a block-local reduction.  dE = (g - e (e . g)) / ||E||.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_grad_combine_unit(const CombineArgs a, int tpr) {
+  constexpr int W = VEC ? 8 : 1;
+  const int per_row = (a.D + W - 1) / W;
+  const int rows_per_block = 256 / tpr;
+  const int r_local = (int)threadIdx.x / tpr, t_in_row = (int)threadIdx.x - r_local * tpr;
+  const int64_t row = (int64_t)blockIdx.x * rows_per_block + r_local;
+  const bool active = r_local < rows_per_block && row < a.n && t_in_row < per_row;
+  const int d = t_in_row * W;
+  float g[8], e[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] = e[i] = 0.f;
+  float inv = 0.f, dot = 0.f;
+  if (active) {
+    combine_terms<VEC>(a, row, d, g);
+    inv = __ldg(a.unit_inv + row);
+    if (VEC) scb_ld8(a.unit_src, a.unit_dtype, row * a.ld_unit + d, e);
+    else e[0] = scb_ld(a.unit_src, a.unit_dtype, row * a.ld_unit + d);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      e[i] *= inv;
+      dot = fmaf(e[i], g[i], dot);
+    }
+  }
+  dot = scb_warp_sum(dot);
+  __shared__ float wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (!active) return;
+  const int w0 = r_local * (tpr >> 5);
+  float tot = 0.f;
+  for (int w = 0; w < (tpr >> 5); ++w) tot += wsum[w0 + w];      // fixed order: bit-reproducible
+#pragma unroll
+  for (int i = 0; i < W; ++i) g[i] = (g[i] - e[i] * tot) * inv;
+  combine_store<VEC>(a, row, d, g);
 }
 
 }  // namespace
@@ -687,18 +742,33 @@ extern "C" int scb_grad_combine(const void* X, const void* Y, int64_t n, int D, 
                                 const float* diag, float scale, float a_coef, const float* u_out, int u_jparts,
                                 const float* rq, int rq_parts, float u_coef, const float* u_dev_coef, float l_coef,
                                 const float* extra, float e_coef, const float* dev_scale, void* dX, int out_dtype,
-                                int64_t ldOut, const float* scale_dev, void* stream) {
+                                int64_t ldOut, const float* scale_dev, const void* unit_src, int64_t ld_unit, int unit_dtype,
+                                const float* unit_inv, void* stream) {
   SCB_COMMON_CHECKS(X && dX, n, D, dtype);
   SCB_CHECK_ARG(scb_dtype_ok(out_dtype) && ldOut >= D, SCB_E_ARG, "grad_combine: bad output layout");
   SCB_CHECK_ARG(!a_out || (Y && row_lse && col_lse_rows && diag && a_jparts > 0), SCB_E_ARG, "grad_combine: anchor term");
   SCB_CHECK_ARG(!u_out || (rq && rq_parts > 0 && u_jparts > 0), SCB_E_ARG, "grad_combine: L_unif term");
   SCB_CHECK_ARG(l_coef == 0.f || Y, SCB_E_ARG, "grad_combine: L_align term needs Y");
   if (n == 0) return 0;
+  SCB_CHECK_ARG(!unit_src == !unit_inv, SCB_E_ARG, "grad_combine: the fused normalise needs both the rows and 1/norm");
+  SCB_CHECK_ARG(!unit_src || (scb_dtype_ok(unit_dtype) && ld_unit >= D), SCB_E_ARG, "grad_combine: bad layout of the un-normalised rows");
   CombineArgs a{X, Y, n, D, ldX, ldY, dtype, a_out, a_jparts, row_lse, col_lse_rows, diag, scale, a_coef, u_out, u_jparts,
-                rq, rq_parts, u_coef, u_dev_coef, l_coef, extra, e_coef, dev_scale, dX, out_dtype, ldOut, scale_dev};
+                rq, rq_parts, u_coef, u_dev_coef, l_coef, extra, e_coef, dev_scale, dX, out_dtype, ldOut, scale_dev,
+                unit_src, ld_unit, unit_dtype, unit_inv};
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = vec_ok(X, ldX, D) && (!Y || vec_ok(Y, ldY, D)) && scb_aligned16(dX) && ldOut % 8 == 0 &&
-                   (!extra || scb_aligned16(extra));
+                   (!extra || scb_aligned16(extra)) && (!unit_src || vec_ok(unit_src, ld_unit, D));
+  if (unit_src) {          // a row per `tpr` threads of one block (whole warps): D <= 2048 vectorised, D <= 256 otherwise
+    const int per_row_u = vec ? D / 8 : D;
+    const int tpr = ((per_row_u + 31) / 32) * 32;
+    SCB_CHECK_ARG(tpr <= 256, SCB_E_SHAPE, "grad_combine: the fused normalise needs D <= 2048 (D <= 256 for unaligned rows), D=%d", D);
+    const int64_t rows_per_block = 256 / tpr;
+    const unsigned grid_u = (unsigned)((n + rows_per_block - 1) / rows_per_block);
+    if (vec) k_grad_combine_unit<true><<<grid_u, 256, 0, s>>>(a, tpr);
+    else k_grad_combine_unit<false><<<grid_u, 256, 0, s>>>(a, tpr);
+    SCB_CHECK_LAUNCH("grad_combine (fused normalise)");
+    return 0;
+  }
   const int per_row = vec ? D / 8 : D;
   const int64_t total = n * per_row;
   const unsigned grid = (unsigned)((total + 255) / 256);

@@ -11,7 +11,7 @@ get_alpha).  Behaviour is reproduced AS CODED:
   * an unknown loss_type is an error (the reference dies at loss.item() one line later).
 """
 from .losses import (contrastive_loss, lalign_loss, lunif_loss, normalized_centroids, centroid_operand_dtype,
-                     fused_terms_loss)
+                     fused_terms_loss, l2_normalize)
 
 __all__ = ["get_beta", "get_alpha", "ladder_weights", "compose_loss", "weighted_loss", "set_fused", "LOSS_TYPES"]
 
@@ -87,11 +87,16 @@ def set_fused(flag):
     return prev
 
 
-def weighted_loss(image_embeds, text_embeds, temperature, w, *, group=None):
-    """sum of the selected terms; a zero weight skips the kernel (its gradient is exactly 0)."""
+def weighted_loss(image_embeds, text_embeds, temperature, w, *, group=None, normalize=False):
+    """sum of the selected terms; a zero weight skips the kernel (its gradient is exactly 0).
+    normalize=True: the embeddings are the encoders' raw outputs and the pre-loss normalise of the training loop
+    (sparsify_clip.py:772-773) is part of this call -- inside the fused node, where its backward rides on the gradient
+    combine pass; as a separate l2_normalize in front of the modular path."""
     if _fuse and any(w[k] != 0.0 for k in ("anchor", "align", "unif_img", "unif_txt", "unif_cen")):
         return fused_terms_loss(image_embeds, text_embeds, temperature, w["anchor"], w["align"], w["unif_img"],
-                                w["unif_txt"], w_unif_cen=w["unif_cen"], group=group)
+                                w["unif_txt"], w_unif_cen=w["unif_cen"], group=group, normalize=normalize)
+    if normalize:
+        image_embeds, text_embeds = l2_normalize(image_embeds), l2_normalize(text_embeds)
     loss = None
 
     def add(acc, wt, term):
@@ -114,7 +119,9 @@ def weighted_loss(image_embeds, text_embeds, temperature, w, *, group=None):
     return loss
 
 
-def compose_loss(config, image_embeds, text_embeds, temperature, epoch=0, current_batch=1, t_total=100, *, group=None):
-    """The per-batch loss of the reference training loop for config["loss_type"]."""
+def compose_loss(config, image_embeds, text_embeds, temperature, epoch=0, current_batch=1, t_total=100, *, group=None,
+                 normalize=False):
+    """The per-batch loss of the reference training loop for config["loss_type"] (normalize=True: from the encoders'
+    raw outputs, sparsify_clip.py:768-773 included)."""
     return weighted_loss(image_embeds, text_embeds, temperature,
-                         ladder_weights(config, epoch, current_batch, t_total), group=group)
+                         ladder_weights(config, epoch, current_batch, t_total), group=group, normalize=normalize)

@@ -260,10 +260,19 @@ class _FusedTermsFn(torch.autograd.Function):
     forward (L_unif yields it in the same sweep as its value anyway); backward multiplies by grad_output."""
 
     @staticmethod
-    def forward(ctx, I, T, tau_t, tau_f, w_a, w_l, w_i, w_t, w_c, t_unif, group):
+    def forward(ctx, I, T, tau_t, tau_f, w_a, w_l, w_i, w_t, w_c, t_unif, group, normalize=False):
         be = get_backend()
         I, T = _common(I, T)
-        Ip, Tp = be.prep(I), be.prep(T)
+        E_I = E_T = inv_I = inv_T = None
+        if normalize:
+            # the pre-loss normalise of the training loop (sparsify_clip.py:772-773, no eps) inside the node: the terms are
+            # evaluated on e / ||e|| (written in the operand dtype from the un-rounded rows), and the combine pass of
+            # backward pulls the gradient back to e itself (scb_grad_combine, unit_src / unit_inv)
+            E_I, E_T = be.prep(I, cast_fp32=False), be.prep(T, cast_fp32=False)
+            op_dt = be.prep(I[:1]).dtype
+            (Ip, inv_I), (Tp, inv_T) = be.normalize_fwd(E_I, op_dt), be.normalize_fwd(E_T, op_dt)
+        else:
+            Ip, Tp = be.prep(I), be.prep(T)
         rank, ws = _world(group)
         n, D = Ip.shape
         B = n * ws
@@ -430,7 +439,7 @@ class _FusedTermsFn(torch.autograd.Function):
         ctx.need = (need_I, need_T)
         # every tensor the backward reads goes through save_for_backward (autograd's version counters then catch an
         # in-place update of the embeddings between forward and backward); the dict structure is rebuilt from a spec
-        flat, ctx.spec = _flatten((Ip, Tp, an_I, an_T, un_I, un_T, 2.0 * w_l / B, cen, dtau))
+        flat, ctx.spec = _flatten((Ip, Tp, an_I, an_T, un_I, un_T, 2.0 * w_l / B, cen, dtau, E_I, E_T, inv_I, inv_T))
         ctx.save_for_backward(*flat)
         return loss
 
@@ -438,30 +447,40 @@ class _FusedTermsFn(torch.autograd.Function):
     def backward(ctx, gout):
         be = get_backend()
         g = _gout32(gout)
-        Ip, Tp, an_I, an_T, un_I, un_T, lc, cen, dtau0 = _unflatten(ctx.saved_tensors, ctx.spec)
+        Ip, Tp, an_I, an_T, un_I, un_T, lc, cen, dtau0, E_I, E_T, inv_I, inv_T = _unflatten(ctx.saved_tensors, ctx.spec)
         dI = dT = dtau = None
+
+        def combine(X, Y, k, an, un, E, inv):
+            if E is None:
+                return be.grad_combine(X, Y, ctx.out_dtypes[k], anchor=an, unif=un, l_coef=lc, dev_scale=g, extra=cen,
+                                       e_coef=1.0).to(ctx.in_dtypes[k])
+            if be.can_fuse_normalize(X, E):          # one pass: every term, then the backward of e -> e / ||e||
+                return be.grad_combine(X, Y, ctx.out_dtypes[k], anchor=an, unif=un, l_coef=lc, dev_scale=g, extra=cen,
+                                       e_coef=1.0, unit=(E, inv)).to(ctx.in_dtypes[k])
+            g32 = be.grad_combine(X, Y, torch.float32, anchor=an, unif=un, l_coef=lc, dev_scale=g, extra=cen, e_coef=1.0)
+            return be.normalize_bwd(E, g32, inv).to(ctx.in_dtypes[k])
+
         if ctx.need[0]:
-            dI = be.grad_combine(Ip, Tp, ctx.out_dtypes[0], anchor=an_I, unif=un_I, l_coef=lc, dev_scale=g,
-                                 extra=cen, e_coef=1.0).to(ctx.in_dtypes[0])
+            dI = combine(Ip, Tp, 0, an_I, un_I, E_I, inv_I)
         if ctx.need[1]:
-            dT = be.grad_combine(Tp, Ip, ctx.out_dtypes[1], anchor=an_T, unif=un_T, l_coef=lc, dev_scale=g,
-                                 extra=cen, e_coef=1.0).to(ctx.in_dtypes[1])
+            dT = combine(Tp, Ip, 1, an_T, un_T, E_T, inv_T)
         if dtau0 is not None:
             dt, tdev, shp = ctx.tau_meta
             dtau = (dtau0 * g.to(device=dtau0.device, dtype=dtau0.dtype)).to(device=tdev, dtype=dt).reshape(shp)
-        return dI, dT, dtau, None, None, None, None, None, None, None, None
+        return dI, dT, dtau, None, None, None, None, None, None, None, None, None
 
 
 def fused_terms_loss(image_embeds, text_embeds, temperature=0.07, w_anchor=1.0, w_align=0.0, w_unif_img=0.0,
-                     w_unif_txt=0.0, t=2, *, w_unif_cen=0.0, group=None):
+                     w_unif_txt=0.0, t=2, *, w_unif_cen=0.0, group=None, normalize=False):
     """w_anchor * contrastive_loss + w_align * lalign_loss + w_unif_img * lunif_loss(I) + w_unif_txt * lunif_loss(T)
     + w_unif_cen * lunif_loss(normalized_centroids(I, T)), evaluated as one fused autograd node (see _FusedTermsFn).
-    Zero weights skip their kernels."""
+    Zero weights skip their kernels.  normalize=True: the inputs are the encoders' un-normalised outputs; the node
+    applies the training loop's pre-loss normalise (sparsify_clip.py:772-773) and its backward itself."""
     group = _resolve_group(group)
     tt = temperature if isinstance(temperature, torch.Tensor) else None
     tf = None if tt is not None else float(temperature)
     return _FusedTermsFn.apply(image_embeds, text_embeds, tt, tf, float(w_anchor), float(w_align), float(w_unif_img),
-                               float(w_unif_txt), float(w_unif_cen), t, group)
+                               float(w_unif_txt), float(w_unif_cen), t, group, bool(normalize))
 
 
 # ----------------------------------------------------------------------------- L_align

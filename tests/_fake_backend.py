@@ -118,7 +118,12 @@ class FakeBackend:
         W[idx, idx + diag_off] = 0
         return {"out": (W @ Ball)[None], "jparts": 1, "ws": ws}
 
-    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None, extra=None, e_coef=0.0):
+    @staticmethod
+    def can_fuse_normalize(X, E):
+        return X.shape[1] % 8 == 0          # exercise both routes of the fused node's backward
+
+    def grad_combine(self, X, Y, out_dtype, anchor=None, unif=None, l_coef=0.0, dev_scale=None, extra=None, e_coef=0.0,
+                     unit=None):
         g = l_coef * (X - Y) if l_coef != 0.0 else torch.zeros_like(X)
         if extra is not None:
             g = g + e_coef * extra
@@ -134,6 +139,10 @@ class FakeBackend:
             g = g + uc * (rq[:, None] * X - U)
         if dev_scale is not None:
             g = g * dev_scale.double()
+        if unit is not None:                 # dE = (g - e (e . g)) / ||E||
+            E, inv = unit
+            e = E * inv[:, None]
+            g = (g - e * (e * g).sum(1, keepdim=True)) * inv[:, None]
         return g.to(out_dtype)
 
     def lunif_core(self, Xr, Xall, t, row_offset, need_grad, sqn_r=None, sqn_all=None, sum_out=None):

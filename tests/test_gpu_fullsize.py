@@ -174,6 +174,58 @@ def test_l2_normalize_then_loss_chain_gradient():
         assert np.linalg.norm(got.double().cpu().numpy() - want) <= 1e-5 * scale, (np.linalg.norm(want), scale)
 
 
+@pytest.mark.parametrize("B,D,dtype,mode,tol", [
+    (384, 512, torch.float32, "exact", 1e-5),      # 64 threads per row, 4 rows per block
+    (301, 768, torch.float32, "exact", 1e-5),      # 96 threads per row: 2 rows per block, 64 idle threads, row tail
+    (257, 1024, torch.float32, "bf16", 1e-3),      # tensor-core path: fp32 encoder outputs, bf16 operands
+    (130, 44, torch.float32, "exact", 1e-5),       # D % 8 != 0: one column per thread
+    (300, 264, torch.bfloat16, "exact", 4e-3),     # bf16 leaves (the returned gradient is itself rounded to 8 bits)
+    (129, 2048, torch.float32, "exact", 1e-5),     # 256 threads per row
+    (64, 2056, torch.float32, "exact", 1e-5),      # beyond one block per row: the separate normalise backward
+])
+def test_normalize_fused_into_the_composition(B, D, dtype, mode, tol):
+    """weighted_loss(..., normalize=True) on RAW encoder outputs (sparsify_clip.py:768-773 inside the fused node; its
+    backward rides on the gradient combine pass, scb_grad_combine unit_src / unit_inv) against the oracle chain
+    cf.weighted_loss -> cf.l2_normalize_backward, and against the explicit l2_normalize -> weighted_loss chain."""
+    tau = 0.1
+    g = torch.Generator(device="cuda").manual_seed(B + D)
+    e_i = (torch.randn(B, D, generator=g, device="cuda") * (0.5 + 3.0 * torch.rand(B, 1, generator=g, device="cuda"))).to(dtype)
+    e_t = (e_i.float() + 1.5 * torch.randn(B, D, generator=g, device="cuda")).to(dtype)
+    w = dict(anchor=1.0, align=1.0, unif_img=0.5, unif_txt=0.0, unif_cen=1.0)
+    prev = scb.set_fp32_mode(mode)
+    try:
+        xi, xt = e_i.clone().requires_grad_(True), e_t.clone().requires_grad_(True)
+        loss = scb.weighted_loss(xi, xt, tau, w, normalize=True)
+        (loss * 4.0).backward()
+        yi, yt = e_i.clone().requires_grad_(True), e_t.clone().requires_grad_(True)
+        loss2 = scb.weighted_loss(scb.l2_normalize(yi), scb.l2_normalize(yt), tau, w)
+        (loss2 * 4.0).backward()
+        op_dt = scb.operand_dtype(e_i)          # what the B x B passes read: the normalised rows are WRITTEN in this dtype
+    finally:
+        scb.set_fp32_mode(prev)
+
+    def unit_rows_as_the_kernels_see_them(e):
+        y = e.float()
+        return (y * (1.0 / y.norm(dim=1, keepdim=True))).to(op_dt).double().cpu().numpy()
+
+    # the oracle gets identical inputs: the terms at the (rounded) unit rows, then the exact pull-back through e -> e / |e|
+    ei, et = e_i.double().cpu().numpy(), e_t.double().cpu().numpy()
+    ref, dI, dT, _, terms = cf.weighted_loss(unit_rows_as_the_kernels_see_them(e_i), unit_rows_as_the_kernels_see_them(e_t), tau,
+                                             1.0, 1.0, 0.5, 0.0, 1.0)
+    mag = sum(abs(v) for v in terms.values())
+    assert abs(loss.item() - ref) <= 1e-5 * mag, (loss.item(), ref)
+    # (the explicit chain rounds the RAW rows to the operand dtype before it normalises them: other operands, same loss to 2e-3)
+    assert abs(loss2.item() - ref) <= 2e-3 * mag
+    for got, got2, e, d in ((xi.grad, yi.grad, ei, dI), (xt.grad, yt.grad, et, dT)):
+        want = cf.l2_normalize_backward(e, d)
+        scale = np.linalg.norm(d / np.linalg.norm(e, axis=1, keepdims=True))      # what goes INTO the projection
+        err = np.linalg.norm(got.double().cpu().numpy() / 4.0 - want)
+        err2 = np.linalg.norm(got2.double().cpu().numpy() / 4.0 - want)
+        print(f"[normalize fused B={B} D={D} {dtype} {mode}] inside the node {err / scale:.2e}, explicit chain {err2 / scale:.2e}")
+        assert err <= tol * scale, (err / scale, err2 / scale)
+        assert torch.isfinite(got).all()
+
+
 def test_random_alignment_loss_draws_from_the_cpu_generator_like_the_reference():
     """sparsify_clip.py:181 draws torch.randperm on the CPU generator; the same seed must give the same permutation."""
     I, T = _synth(256, 64)

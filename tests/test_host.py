@@ -88,10 +88,14 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.scb_loss_assemble(None, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, p, p, None, None) == -1
     # the fused combine: a term's inputs must come together, the output layout must hold a row
     assert lib.scb_grad_combine(p, None, 4, 8, 8, 8, _lib.SCB_BF16, p, 1, None, None, None, 1.0, 1.0, None, 0, None, 0, 0.0,
-                                None, 0.0, None, 0.0, None, p, _lib.SCB_BF16, 8, None, None) == -1
+                                None, 0.0, None, 0.0, None, p, _lib.SCB_BF16, 8, None, None, 0, 0, None, None) == -1
     assert b"anchor" in lib.scb_last_error()
     assert lib.scb_grad_combine(p, p, 4, 8, 8, 8, _lib.SCB_BF16, None, 0, None, None, None, 1.0, 1.0, None, 0, None, 0, 0.0,
-                                None, 1.0, None, 0.0, None, p, _lib.SCB_BF16, 4, None, None) == -1
+                                None, 1.0, None, 0.0, None, p, _lib.SCB_BF16, 4, None, None, 0, 0, None, None) == -1
+    # the fused normalise: the un-normalised rows and 1/norm come together
+    assert lib.scb_grad_combine(p, p, 4, 8, 8, 8, _lib.SCB_BF16, None, 0, None, None, None, 1.0, 1.0, None, 0, None, 0, 0.0,
+                                None, 1.0, None, 0.0, None, p, _lib.SCB_BF16, 8, None, p, 8, _lib.SCB_BF16, None, None) == -1
+    assert b"normalise" in lib.scb_last_error()
     # the SM push of the peer gather: 16-byte granularity of the shard and of every pointer; the plan helper's arguments
     dst = (ctypes.c_void_p * 2)(p, p)
     assert lib.scb_peer_push_sm(p, 24, dst, 2, f, p, 2, f, None) == -1 and b"16-byte" in lib.scb_last_error()
@@ -243,6 +247,41 @@ def test_single_process_fake_backend_matches_oracle(fused):
         # the fused node keeps its scalar partial sums in fp32 (they travel in the packed gather when sharded)
         assert loss.item() == pytest.approx(ref_loss, rel=1e-6 if fused else 1e-12)
         assert np.abs(I.grad.numpy() - dI).max() < 1e-6 and np.abs(T.grad.numpy() - dT).max() < 1e-6
+    finally:
+        scb.set_fused(pf)
+        backend_cuda.set_backend(prev)
+
+
+@pytest.mark.parametrize("fused,D", [(True, 8), (True, 12), (False, 8)])
+def test_normalize_inside_the_composition_matches_the_explicit_chain(fused, D):
+    """compose_loss(..., normalize=True) on un-normalised encoder outputs (sparsify_clip.py:768-773 inside the call) ==
+    compose_loss on l2_normalize(...) of them, value and gradients w.r.t. the un-normalised rows; both routes of the
+    fused node's backward (normalise backward inside the combine pass when D % 8 == 0, as a separate pass otherwise)
+    and the modular path; the gradient is also checked against the oracle's normalise backward."""
+    prev = backend_cuda.set_backend(FakeBackend())
+    pf = scb.set_fused(fused)
+    try:
+        g = torch.Generator().manual_seed(5)
+        E_I = (torch.randn(19, D, generator=g, dtype=torch.float64) * (0.5 + 3.0 * torch.rand(19, 1, generator=g, dtype=torch.float64)))
+        E_T = E_I + 0.7 * torch.randn(19, D, generator=g, dtype=torch.float64)
+        cfg = {"loss_type": "only_lunif_n_then_anchor+lalign+lunif(text)+lunif(img)", "only_lunif_epochs": 0}
+        got = []
+        for inside in (True, False):
+            a, b = E_I.clone().requires_grad_(True), E_T.clone().requires_grad_(True)
+            if inside:
+                loss = scb.compose_loss(cfg, a, b, 0.1, epoch=1, current_batch=10, t_total=100, normalize=True)
+            else:
+                loss = scb.compose_loss(cfg, scb.l2_normalize(a), scb.l2_normalize(b), 0.1, epoch=1, current_batch=10, t_total=100)
+            (loss * 3.0).backward()
+            got.append((loss.item(), a.grad.numpy() / 3.0, b.grad.numpy() / 3.0))
+        assert got[0][0] == pytest.approx(got[1][0], rel=1e-12)
+        # (the explicit chain hands the loss node's gradient to the normalise node as fp32: 1e-8 relative)
+        assert np.abs(got[0][1] - got[1][1]).max() < 1e-7 and np.abs(got[0][2] - got[1][2]).max() < 1e-7
+        yI, yT = cf.l2_normalize(E_I.numpy()), cf.l2_normalize(E_T.numpy())
+        ref_loss, dyI, dyT, _, _ = cf.compose_loss(cfg, yI, yT, 0.1, 1, 10, 100)
+        assert got[0][0] == pytest.approx(ref_loss, rel=1e-6)
+        assert np.abs(got[0][1] - cf.l2_normalize_backward(E_I.numpy(), dyI)).max() < 1e-6
+        assert np.abs(got[0][2] - cf.l2_normalize_backward(E_T.numpy(), dyT)).max() < 1e-6
     finally:
         scb.set_fused(pf)
         backend_cuda.set_backend(prev)
